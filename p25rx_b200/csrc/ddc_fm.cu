@@ -1,0 +1,292 @@
+// ddc_fm.cu -- K1: IQ -> 48 kHz C4FM baseband for many streams in one launch.
+//
+// Replaces one iteration of DemodTask::run for every stream (reference src/demod.rs:70-117):
+//   u8 IQ -> Complex32 table        src/demod.rs:82-84   (rtlsdr_iq::IQ)
+//   /5 decimating FIR               src/demod.rs:87      (static_decimate::Decimator<DecimFir>)
+//   channel-select FIR              src/demod.rs:93      (static_fir::FirFilter<BandpassFir>)
+//   power accumulation              src/demod.rs:95-101, :123-134
+//   FM discriminator                src/demod.rs:109-111 (demod_fm::FmDemod::new(5000, 48000))
+//   10-tap moving average           src/demod.rs:114     (moving_avg::MovingAverage::new(10))
+// plus a /10 front stage for 2.4 MS/s input (BASELINE.json configs[0]; declared extension).
+//
+// Design.  The whole chain is non-recursive, so every output is a pure function of a window of
+// the logical input (tail of the previous chunk ++ this chunk).  A CTA owns one (stream, segment)
+// and streams through it in blocks: the block is staged in shared memory with coalesced 16-byte
+// loads, then each decimating stage runs *input-stationary*: a thread reads its own D consecutive
+// inputs once (conflict-free LDS.128 / LDS.64), forms the Q partial sums that those inputs
+// contribute to the next Q outputs with the taps as constant-bank operands, and neighbouring
+// partials are combined through shared memory.  Every staged input is therefore read from shared
+// memory exactly once.  The 48 kHz stages (channel FIR, discriminator, boxcar) use power-of-two
+// rings.  A segment starts one block early to warm the rings up, so segments are independent and
+// the only carried state is the raw input tail.
+//
+// HBM-bound by design: algorithmic traffic 8 + 4/D bytes per cf32 input sample.
+#include "p25cu_internal.cuh"
+
+__constant__ float c_taps_front[P25_TAPS_FRONT];
+__constant__ float c_taps_decim[P25_TAPS_DECIM];
+__constant__ float c_taps_chan[P25_TAPS_CHAN];
+__constant__ float c_iq_lut[256];
+
+static_assert(P25_TAPS_FRONT == 5 * P25_DECIM_FRONT, "front stage is a 10-phase x 5-tap polyphase matrix");
+static_assert(P25_TAPS_DECIM == 5 * P25_DECIM_NATIVE, "decimator is a 5-phase x 5-tap polyphase matrix");
+
+template <bool FRONT>
+struct Cfg {
+    static constexpr int MB = FRONT ? 64 : 256;         // 48 kHz outputs per block
+    static constexpr int NT = FRONT ? 320 : 256;        // threads
+    static constexpr int DIN = FRONT ? 50 : 5;          // input samples per output
+    static constexpr int XN = MB * DIN;                 // input samples per block
+    static constexpr int ACOLS = FRONT ? 5 * MB : 0;    // front-stage outputs per block
+    static constexpr int RING = FRONT ? 128 : 512;      // >= MB + 40
+    static constexpr int HT = FRONT ? 3264 : 1312;      // input tail carried between chunks
+};
+
+template <bool FRONT>
+struct Smem {
+    using C = Cfg<FRONT>;
+    float2 xs[C::XN];                        // staged input block
+    float2 pa[2][4][FRONT ? C::ACOLS : 1];   // front-stage partial sums (ping-pong)
+    float ya_re[FRONT ? C::ACOLS : 1], ya_im[FRONT ? C::ACOLS : 1];
+    float2 pd[2][4][C::MB];                  // decimator partial sums (ping-pong)
+    float yd_re[C::RING], yd_im[C::RING];    // decimator output ring
+    float c_re[C::RING], c_im[C::RING];      // channel filter output ring
+    float d[C::RING];                        // discriminator output ring
+    float red[32];
+};
+
+__device__ __forceinline__ float2 cf_from_u8(uchar2 b) { return make_float2(c_iq_lut[b.x], c_iq_lut[b.y]); }
+
+// logical input sample l (0 .. HT+n): tail of the previous chunk, then this chunk; zeros beyond
+template <int FMT>
+__device__ __forceinline__ float2 load_logical(const DdcParams& p, const float2* tail, const void* chunk, long long l) {
+    if (l < (long long)p.ht) return tail[l];
+    const long long i = l - p.ht;
+    if (i >= (long long)p.n) return make_float2(0.f, 0.f);
+    if (FMT == P25CU_FMT_CF32_IQ) return __ldcs((const float2*)chunk + i);
+    return cf_from_u8(__ldcs((const uchar2*)chunk + i));
+}
+
+template <bool FRONT, int FMT>
+__device__ __forceinline__ void stage_block(Smem<FRONT>& sm, const DdcParams& p, const float2* tail, const void* chunk,
+                                            long long l0) {
+    using C = Cfg<FRONT>;
+    if (FMT == P25CU_FMT_CF32_IQ && p.aligned16) {
+        // 16-byte path: two samples per load; pairs never straddle tail/chunk or the chunk end
+        for (int i = 2 * threadIdx.x; i < C::XN; i += 2 * C::NT) {
+            const long long l = l0 + i;
+            float4 v;
+            if (l < (long long)p.ht) {
+                v = *(const float4*)(tail + l);
+            } else {
+                const long long j = l - p.ht;
+                v = j < (long long)p.n ? __ldcs((const float4*)((const float2*)chunk + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            *(float4*)(&sm.xs[i]) = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < C::XN; i += C::NT) sm.xs[i] = load_logical<FMT>(p, tail, chunk, l0 + i);
+    }
+}
+
+// partial sums of one polyphase column: P_q = sum_p h[D*q + p] * x[D-1-p],  q = 0..4
+template <int D>
+__device__ __forceinline__ void column_partials(const float2 (&x)[D], const float* __restrict__ h, float2 (&P)[5]) {
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        float re = 0.f, im = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < D; pp++) {
+            const float t = h[D * q + pp];
+            re = fmaf(t, x[D - 1 - pp].x, re);
+            im = fmaf(t, x[D - 1 - pp].y, im);
+        }
+        P[q] = make_float2(re, im);
+    }
+}
+
+template <bool FRONT, int FMT>
+__global__ void __launch_bounds__(Cfg<FRONT>::NT) p25_ddc_fm_kernel(const DdcParams p) {
+    using C = Cfg<FRONT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<FRONT>& sm = *reinterpret_cast<Smem<FRONT>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const unsigned s = blockIdx.x / p.n_seg, g = blockIdx.x % p.n_seg;
+
+    // zero rings and partial buffers (everything behind xs)
+    {
+        float* z = reinterpret_cast<float*>(&sm.pa[0][0][0]);
+        const int nz = (int)((sizeof(Smem<FRONT>) - sizeof(sm.xs)) / sizeof(float));
+        for (int i = tid; i < nz; i += C::NT) z[i] = 0.f;
+    }
+
+    const float2* tail = p.tail_in + (size_t)s * p.ht;
+    const void* chunk = (FMT == P25CU_FMT_CF32_IQ) ? (const void*)((const float2*)p.iq + (size_t)s * p.n)
+                                                    : (const void*)((const uchar2*)p.iq + (size_t)s * p.n);
+    float* out = p.bb + (size_t)s * p.row_stride + P25CU_BB_HIST;
+
+    const long long M0 = (long long)p.m0;
+    const long long mb = M0 + (long long)g * p.seg_out;
+    long long me = mb + p.seg_out;
+    if (me > M0 + (long long)p.n_out) me = M0 + p.n_out;
+    const long long a0 = (long long)p.a0;
+    float pw = 0.f;
+    int pb = 0;
+    __syncthreads();
+
+    for (long long mi = mb - C::MB; mi < me; mi += C::MB, pb ^= 1) {
+        // 1. stage the input block [DIN*mi, DIN*(mi+MB)) of the logical input
+        stage_block<FRONT, FMT>(sm, p, tail, chunk, (long long)C::DIN * mi - a0 + (long long)p.ht);
+        __syncthreads();
+
+        if constexpr (FRONT) {
+            // 2. front /10 stage, input-stationary: thread = one column of 10 inputs
+            float2 P[5];
+            {
+                float2 x[10];
+                const float4* src = reinterpret_cast<const float4*>(&sm.xs[10 * tid]);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    const float4 v = src[i];
+                    x[2 * i] = make_float2(v.x, v.y);
+                    x[2 * i + 1] = make_float2(v.z, v.w);
+                }
+                column_partials<10>(x, c_taps_front, P);
+            }
+#pragma unroll
+            for (int q = 1; q < 5; q++) sm.pa[pb][q - 1][tid] = P[q];
+            __syncthreads();
+            // 3. combine with the partials of the 4 previous columns
+            float re = P[0].x, im = P[0].y;
+#pragma unroll
+            for (int q = 1; q < 5; q++) {
+                const int c = tid - q;
+                const float2 v = c >= 0 ? sm.pa[pb][q - 1][c] : sm.pa[pb ^ 1][q - 1][C::ACOLS + c];
+                re += v.x;
+                im += v.y;
+            }
+            sm.ya_re[tid] = re;
+            sm.ya_im[tid] = im;
+            __syncthreads();
+        }
+
+        // 4. /5 decimator, input-stationary: thread = one column of 5 inputs (one 48 kHz output)
+        float2 Q[5];
+        if (tid < C::MB) {
+            float2 x[5];
+            if constexpr (FRONT) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) x[i] = make_float2(sm.ya_re[5 * tid + i], sm.ya_im[5 * tid + i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 5; i++) x[i] = sm.xs[5 * tid + i];
+            }
+            column_partials<5>(x, c_taps_decim, Q);
+#pragma unroll
+            for (int q = 1; q < 5; q++) sm.pd[pb][q - 1][tid] = Q[q];
+        }
+        __syncthreads();
+        if (tid < C::MB) {
+            float re = Q[0].x, im = Q[0].y;
+#pragma unroll
+            for (int q = 1; q < 5; q++) {
+                const int c = tid - q;
+                const float2 v = c >= 0 ? sm.pd[pb][q - 1][c] : sm.pd[pb ^ 1][q - 1][C::MB + c];
+                re += v.x;
+                im += v.y;
+            }
+            const unsigned r = (unsigned)(mi + tid) & (C::RING - 1);
+            sm.yd_re[r] = re;
+            sm.yd_im[r] = im;
+        }
+        __syncthreads();
+
+        // 5. channel-select FIR at 48 kHz: one (output, component) per work item
+        for (int w = tid; w < 2 * C::MB; w += C::NT) {
+            const int o = w < C::MB ? w : w - C::MB;
+            const float* src = w < C::MB ? sm.yd_re : sm.yd_im;
+            const unsigned r = (unsigned)(mi + o);
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < P25_TAPS_CHAN; k++) acc = fmaf(c_taps_chan[k], src[(r - k) & (C::RING - 1)], acc);
+            (w < C::MB ? sm.c_re : sm.c_im)[r & (C::RING - 1)] = acc;
+        }
+        __syncthreads();
+
+        // 6. FM discriminator (+ power of the channel-filtered samples)
+        if (tid < C::MB) {
+            const long long m = mi + tid;
+            const unsigned r = (unsigned)m;
+            const float cr = sm.c_re[r & (C::RING - 1)], ci = sm.c_im[r & (C::RING - 1)];
+            const float pr = sm.c_re[(r - 1) & (C::RING - 1)], pi = sm.c_im[(r - 1) & (C::RING - 1)];
+            const float re = cr * pr + ci * pi;
+            const float im = ci * pr - cr * pi;
+            sm.d[r & (C::RING - 1)] = atan2f(im, re) * P25_FM_GAIN;
+            if (m >= mb && m < me) pw += cr * cr + ci * ci;
+        }
+        __syncthreads();
+
+        // 7. symbol-period boxcar, store
+        if (tid < C::MB) {
+            const long long m = mi + tid;
+            if (m >= mb && m < me) {
+                const unsigned r = (unsigned)m;
+                float acc = 0.f;
+#pragma unroll
+                for (int i = P25_BOXCAR - 1; i >= 0; i--) acc += sm.d[(r - i) & (C::RING - 1)];
+                out[m - M0] = acc / (float)P25_BOXCAR;
+            }
+        }
+        // the next block's first barrier orders these ring reads before they are overwritten
+    }
+
+    // power: block reduction, one atomic per CTA
+    if (p.power_sum) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pw += __shfl_xor_sync(0xFFFFFFFFu, pw, o);
+        __syncthreads();
+        if ((tid & 31) == 0) sm.red[tid >> 5] = pw;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int i = 0; i < C::NT / 32; i++) t += sm.red[i];
+            atomicAdd(p.power_sum + s, t);
+        }
+    }
+
+    // the last segment of each stream writes the input tail for the next chunk
+    if (g == p.n_seg - 1) {
+        float2* tout = p.tail_out + (size_t)s * p.ht;
+        for (int i = tid; i < (int)p.ht; i += C::NT) tout[i] = load_logical<FMT>(p, tail, chunk, (long long)p.n + i);
+    }
+}
+
+unsigned p25cu_ddc_tail_len(int decimation) { return decimation == 50 ? Cfg<true>::HT : Cfg<false>::HT; }
+
+cudaError_t p25cu_ddc_upload_taps() {
+    cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(c_taps_front, P25_TAPS_FRONT_H, sizeof(c_taps_front))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_taps_decim, P25_TAPS_DECIM_H, sizeof(c_taps_decim))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_taps_chan, P25_TAPS_CHAN_H, sizeof(c_taps_chan))) != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_iq_lut, P25_IQ_LUT, sizeof(c_iq_lut));
+}
+
+template <bool FRONT, int FMT>
+static cudaError_t launch(const DdcParams& p, cudaStream_t st) {
+    using C = Cfg<FRONT>;
+    auto kern = p25_ddc_fm_kernel<FRONT, FMT>;
+    const size_t smem = sizeof(Smem<FRONT>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<p.n_streams * p.n_seg, C::NT, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+unsigned p25cu_ddc_block_out(int decimation) { return decimation == 50 ? Cfg<true>::MB : Cfg<false>::MB; }
+
+cudaError_t p25cu_launch_ddc(const DdcParams& p, int format, int decimation, cudaStream_t st) {
+    if (p.n_out == 0 && p.n == 0) return cudaSuccess;
+    if (decimation == 50)
+        return format == P25CU_FMT_CF32_IQ ? launch<true, P25CU_FMT_CF32_IQ>(p, st) : launch<true, P25CU_FMT_U8_IQ>(p, st);
+    return format == P25CU_FMT_CF32_IQ ? launch<false, P25CU_FMT_CF32_IQ>(p, st) : launch<false, P25CU_FMT_U8_IQ>(p, st);
+}

@@ -1,0 +1,406 @@
+// p25cu_api.cu -- the C ABI of include/p25cu.h: context, HBM layout, launch sequencing.
+//
+// Host-side counterpart of the reference's DemodTask (src/demod.rs:44-119) and of the
+// RecvTask / ReplayReceiver sample loops (src/recv.rs:140-167, :204-234; src/replay.rs:26-57),
+// batched over n_streams.  No CPU compute path exists here: every entry point either queues
+// CUDA work or fails with an error code.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "p25cu_internal.cuh"
+
+unsigned p25cu_ddc_block_out(int decimation);
+cudaError_t p25cu_walk_upload_consts();
+
+struct p25cu_ctx {
+    p25cu_config cfg;
+    cudaStream_t stream;
+    char err[512];
+    unsigned ht;               // input tail length (samples)
+    size_t max_out;            // max baseband samples per stream per chunk
+    size_t row_stride;         // floats per baseband row
+    unsigned ev_cap;           // event slots per stream
+    void* d_iq;                // staging for host-resident input (lazy)
+    size_t d_iq_bytes;
+    float2* d_tail[2];
+    int tail_cur;
+    float* d_bb;
+    float* d_power;
+    WalkState* d_states;
+    p25cu_event* d_slots;
+    p25cu_event* d_dense;
+    unsigned* d_offsets;       // [S + 2]: exclusive offsets, total, overflow flag
+    unsigned* d_stats;
+    P25DevTables* d_tables;
+    unsigned long long a_abs;  // input samples consumed per stream
+    unsigned long long p_abs;  // baseband samples decoded per stream
+    size_t last_n_out;
+    bool dev_bb_fresh;
+    unsigned long long launches;
+    int n_sm;
+};
+
+static char g_create_err[512] = "";
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            snprintf(ctx->err, sizeof ctx->err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return P25CU_ERR_CUDA;                                                                       \
+        }                                                                                                \
+    } while (0)
+
+static int fail_arg(p25cu_ctx* ctx, const char* msg) {
+    snprintf(ctx->err, sizeof ctx->err, "%s", msg);
+    return P25CU_ERR_ARG;
+}
+
+extern "C" const char* p25cu_last_error(const p25cu_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" void p25cu_destroy(p25cu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_iq);
+    cudaFree(ctx->d_tail[0]);
+    cudaFree(ctx->d_tail[1]);
+    cudaFree(ctx->d_bb);
+    cudaFree(ctx->d_power);
+    cudaFree(ctx->d_states);
+    cudaFree(ctx->d_slots);
+    cudaFree(ctx->d_dense);
+    cudaFree(ctx->d_offsets);
+    cudaFree(ctx->d_stats);
+    cudaFree(ctx->d_tables);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+static int create_impl(p25cu_ctx* ctx) {
+    const p25cu_config& cfg = ctx->cfg;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (cfg.device < 0 || cfg.device >= ndev) return fail_arg(ctx, "device ordinal out of range");
+    CK(cudaSetDevice(cfg.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg.device));
+    if (prop.major != 10) {
+        snprintf(ctx->err, sizeof ctx->err, "device %d is sm_%d%d; this library is built for sm_100a only", cfg.device,
+                 prop.major, prop.minor);
+        return P25CU_ERR_CUDA;
+    }
+    ctx->n_sm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    const size_t S = cfg.n_streams;
+    ctx->ht = p25cu_ddc_tail_len(cfg.decimation);
+    ctx->max_out = cfg.max_chunk_samples / cfg.decimation + 1;
+    if (cfg.max_baseband > ctx->max_out) ctx->max_out = cfg.max_baseband;
+    ctx->row_stride = (P25CU_BB_HIST + ctx->max_out + 3) & ~(size_t)3;
+    ctx->ev_cap = (unsigned)(ctx->max_out / 200 + 16);
+
+    CK(cudaMalloc(&ctx->d_tail[0], S * ctx->ht * sizeof(float2)));
+    CK(cudaMalloc(&ctx->d_tail[1], S * ctx->ht * sizeof(float2)));
+    CK(cudaMemsetAsync(ctx->d_tail[0], 0, S * ctx->ht * sizeof(float2), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_tail[1], 0, S * ctx->ht * sizeof(float2), ctx->stream));
+    CK(cudaMalloc(&ctx->d_bb, S * ctx->row_stride * sizeof(float)));
+    CK(cudaMemsetAsync(ctx->d_bb, 0, S * ctx->row_stride * sizeof(float), ctx->stream));
+    CK(cudaMalloc(&ctx->d_power, S * sizeof(float)));
+    CK(cudaMalloc(&ctx->d_states, S * sizeof(WalkState)));
+    CK(cudaMemsetAsync(ctx->d_states, 0, S * sizeof(WalkState), ctx->stream));  // state SYNC, pos 0
+    CK(cudaMalloc(&ctx->d_slots, S * ctx->ev_cap * sizeof(p25cu_event)));
+    CK(cudaMalloc(&ctx->d_dense, S * ctx->ev_cap * sizeof(p25cu_event)));
+    CK(cudaMalloc(&ctx->d_offsets, (S + 2) * sizeof(unsigned)));
+    CK(cudaMalloc(&ctx->d_stats, S * P25CU_ST_FAMILIES * 3 * sizeof(unsigned)));
+    CK(cudaMemsetAsync(ctx->d_stats, 0, S * P25CU_ST_FAMILIES * 3 * sizeof(unsigned), ctx->stream));
+    CK(cudaMalloc(&ctx->d_tables, sizeof(P25DevTables)));
+    {
+        P25DevTables* t = new (std::nothrow) P25DevTables;
+        if (!t) return fail_arg(ctx, "out of host memory");
+        memset(t, 0, sizeof *t);
+        p25_fill_tables(t);
+        cudaError_t e = cudaMemcpy(ctx->d_tables, t, sizeof *t, cudaMemcpyHostToDevice);
+        delete t;
+        CK(e);
+    }
+    CK(p25cu_ddc_upload_taps());
+    CK(p25cu_walk_upload_consts());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return P25CU_OK;
+}
+
+extern "C" int p25cu_create(const p25cu_config* cfg, p25cu_ctx** out) {
+    if (!cfg || !out) {
+        snprintf(g_create_err, sizeof g_create_err, "null argument");
+        return P25CU_ERR_ARG;
+    }
+    *out = nullptr;
+    if (cfg->abi_version != P25CU_ABI_VERSION || cfg->n_streams == 0 || cfg->max_chunk_samples == 0 ||
+        (cfg->decimation != 5 && cfg->decimation != 50) ||
+        (cfg->format != P25CU_FMT_U8_IQ && cfg->format != P25CU_FMT_CF32_IQ)) {
+        snprintf(g_create_err, sizeof g_create_err,
+                 "bad config (abi_version %u, n_streams %u, format %d, decimation %d, max_chunk_samples %llu)",
+                 cfg->abi_version, cfg->n_streams, cfg->format, cfg->decimation,
+                 (unsigned long long)cfg->max_chunk_samples);
+        return P25CU_ERR_ARG;
+    }
+    p25cu_ctx* ctx = new (std::nothrow) p25cu_ctx;
+    if (!ctx) return P25CU_ERR_ARG;
+    memset(ctx, 0, sizeof *ctx);
+    ctx->cfg = *cfg;
+    const int rc = create_impl(ctx);
+    if (rc != P25CU_OK) {
+        snprintf(g_create_err, sizeof g_create_err, "%s", ctx->err);
+        p25cu_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return P25CU_OK;
+}
+
+// ---------------------------------------------------------------- Surface 1
+extern "C" int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_device, float* baseband_out, size_t* n_out_p,
+                           float* power_dbm) {
+    if (!ctx) return P25CU_ERR_ARG;
+    if (!iq && n) return fail_arg(ctx, "iq is null");
+    if (n > ctx->cfg.max_chunk_samples) return fail_arg(ctx, "n_in_per_stream exceeds max_chunk_samples");
+    CK(cudaSetDevice(ctx->cfg.device));
+    const size_t S = ctx->cfg.n_streams;
+    const size_t bps = ctx->cfg.format == P25CU_FMT_U8_IQ ? 2 : 8;
+    const void* d_in = iq;
+    if (!iq_on_device && n) {
+        const size_t bytes = S * n * bps;
+        if (bytes > ctx->d_iq_bytes) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_iq);
+            ctx->d_iq = nullptr;
+            ctx->d_iq_bytes = 0;
+            CK(cudaMalloc(&ctx->d_iq, bytes));
+            ctx->d_iq_bytes = bytes;
+        }
+        CK(cudaMemcpyAsync(ctx->d_iq, iq, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_in = ctx->d_iq;
+    }
+    const unsigned D = (unsigned)ctx->cfg.decimation;
+    DdcParams p;
+    memset(&p, 0, sizeof p);
+    p.iq = d_in;
+    p.tail_in = ctx->d_tail[ctx->tail_cur];
+    p.tail_out = ctx->d_tail[ctx->tail_cur ^ 1];
+    p.bb = ctx->d_bb;
+    p.row_stride = ctx->row_stride;
+    p.power_sum = power_dbm ? ctx->d_power : nullptr;
+    p.a0 = ctx->a_abs;
+    p.m0 = ctx->a_abs / D;
+    p.n = (unsigned)n;
+    p.n_out = (unsigned)((ctx->a_abs + n) / D - p.m0);
+    p.n_streams = (unsigned)S;
+    p.ht = ctx->ht;
+    p.aligned16 = ((ctx->a_abs & 1) == 0) && ((n & 1) == 0) && (((uintptr_t)d_in & 15) == 0);
+    {
+        const unsigned mb = p25cu_ddc_block_out(D);
+        const unsigned iters = (p.n_out + mb - 1) / mb;
+        unsigned want = (unsigned)((size_t)ctx->n_sm * 16 / S);
+        unsigned cap = iters / 8;
+        if (want > cap) want = cap;
+        if (want < 1) want = 1;
+        const unsigned per = (iters + want - 1) / want;
+        p.seg_out = (per ? per : 1) * mb;
+        p.n_seg = p.n_out ? (p.n_out + p.seg_out - 1) / p.seg_out : 1;
+    }
+    if (power_dbm) CK(cudaMemsetAsync(ctx->d_power, 0, S * sizeof(float), ctx->stream));
+    if (n) {
+        CK(p25cu_launch_ddc(p, ctx->cfg.format, ctx->cfg.decimation, ctx->stream));
+        ctx->launches++;
+        ctx->tail_cur ^= 1;
+    }
+    ctx->a_abs += n;
+    ctx->last_n_out = p.n_out;
+    ctx->dev_bb_fresh = true;
+    if (n_out_p) *n_out_p = p.n_out;
+    if (baseband_out && p.n_out)
+        CK(cudaMemcpy2DAsync(baseband_out, p.n_out * sizeof(float), ctx->d_bb + P25CU_BB_HIST, ctx->row_stride * sizeof(float),
+                             p.n_out * sizeof(float), S, cudaMemcpyDeviceToHost, ctx->stream));
+    if (power_dbm) {
+        CK(cudaMemcpyAsync(power_dbm, ctx->d_power, S * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (size_t s = 0; s < S; s++) {  // reference src/demod.rs:123-134 with R = 1
+            const float avg = p.n_out ? power_dbm[s] / (float)p.n_out : 0.f;
+            power_dbm[s] = 30.0f + 10.0f * log10f(avg);
+        }
+    } else if (baseband_out) {
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return P25CU_OK;
+}
+
+// ---------------------------------------------------------------- Surface 2
+extern "C" int p25cu_decode(p25cu_ctx* ctx, const float* baseband, size_t n) {
+    if (!ctx) return P25CU_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const size_t S = ctx->cfg.n_streams;
+    if (baseband) {
+        if (n > ctx->max_out) return fail_arg(ctx, "n_per_stream exceeds the configured maximum");
+        if (n)
+            CK(cudaMemcpy2DAsync(ctx->d_bb + P25CU_BB_HIST, ctx->row_stride * sizeof(float), baseband, n * sizeof(float),
+                                 n * sizeof(float), S, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        if (!ctx->dev_bb_fresh) {
+            snprintf(ctx->err, sizeof ctx->err, "p25cu_decode(NULL): no undecoded device-resident baseband (call p25cu_demod first)");
+            return P25CU_ERR_STATE;
+        }
+        n = ctx->last_n_out;
+    }
+    ctx->dev_bb_fresh = false;
+    WalkParams w;
+    memset(&w, 0, sizeof w);
+    w.bb = ctx->d_bb;
+    w.bb_rw = ctx->d_bb;
+    w.row_stride = ctx->row_stride;
+    w.p0 = ctx->p_abs;
+    w.n = (unsigned)n;
+    w.n_streams = (unsigned)S;
+    w.states = ctx->d_states;
+    w.slots = ctx->d_slots;
+    w.ev_cap = ctx->ev_cap;
+    w.stats = ctx->d_stats;
+    w.tables = ctx->d_tables;
+    CK(p25cu_launch_walk(w, ctx->stream));
+    ctx->launches++;
+    ctx->p_abs += n;
+    return P25CU_OK;
+}
+
+extern "C" int p25cu_process(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_device) {
+    const int rc = p25cu_demod(ctx, iq, n, iq_on_device, nullptr, nullptr, nullptr);
+    if (rc != P25CU_OK) return rc;
+    return p25cu_decode(ctx, nullptr, 0);
+}
+
+static int compact(p25cu_ctx* ctx, bool gather, unsigned* total, unsigned* overflow) {
+    const unsigned S = ctx->cfg.n_streams;
+    CK(p25cu_launch_compact(ctx->d_states, ctx->d_slots, ctx->ev_cap, S, ctx->d_offsets, gather ? ctx->d_dense : nullptr,
+                            ctx->stream));
+    ctx->launches += gather ? 2 : 1;
+    unsigned tail[2];
+    CK(cudaMemcpyAsync(tail, ctx->d_offsets + S, sizeof tail, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *total = tail[0];
+    *overflow = tail[1];
+    return P25CU_OK;
+}
+
+extern "C" int p25cu_pending(p25cu_ctx* ctx, size_t* n) {
+    if (!ctx || !n) return P25CU_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    unsigned total, ovf;
+    const int rc = compact(ctx, false, &total, &ovf);
+    if (rc != P25CU_OK) return rc;
+    *n = total;
+    return P25CU_OK;
+}
+
+extern "C" int p25cu_poll(p25cu_ctx* ctx, p25cu_event* out, size_t cap, size_t* n) {
+    if (!ctx || !n || (!out && cap)) return P25CU_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    unsigned total, ovf;
+    const int rc = compact(ctx, true, &total, &ovf);
+    if (rc != P25CU_OK) return rc;
+    const size_t take = total < cap ? total : cap;
+    if (take) {
+        CK(cudaMemcpyAsync(out, ctx->d_dense, take * sizeof(p25cu_event), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    *n = take;
+    if (ovf || take < total) {
+        snprintf(ctx->err, sizeof ctx->err, "event overflow: %u queued, %zu returned, slot overflow %u", total, take, ovf);
+        return P25CU_ERR_OVERFLOW;
+    }
+    return P25CU_OK;
+}
+
+extern "C" int p25cu_resync(p25cu_ctx* ctx, uint32_t stream) {
+    if (!ctx || stream >= ctx->cfg.n_streams) return P25CU_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const unsigned one = 1;
+    CK(cudaMemcpyAsync((char*)(ctx->d_states + stream) + offsetof(WalkState, resync_req), &one, sizeof one,
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return P25CU_OK;
+}
+
+extern "C" int p25cu_get_stats(p25cu_ctx* ctx, uint32_t stream, p25cu_stats* out, int clear) {
+    if (!ctx || !out || stream >= ctx->cfg.n_streams) return P25CU_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    unsigned raw[P25CU_ST_FAMILIES * 3];
+    unsigned* src = ctx->d_stats + (size_t)stream * P25CU_ST_FAMILIES * 3;
+    CK(cudaMemcpyAsync(raw, src, sizeof raw, cudaMemcpyDeviceToHost, ctx->stream));
+    if (clear) CK(cudaMemsetAsync(src, 0, sizeof raw, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int f = 0; f < P25CU_ST_FAMILIES; f++) {
+        out->code[f].words = raw[3 * f];
+        out->code[f].errs = raw[3 * f + 1];
+        out->code[f].size = P25_STATS_SIZE[f];
+        out->code[f].fixed = raw[3 * f + 2];
+    }
+    return P25CU_OK;
+}
+
+// ---------------------------------------------------------------- measurement helpers
+extern "C" void* p25cu_cuda_stream(p25cu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int p25cu_sync(p25cu_ctx* ctx) {
+    if (!ctx) return P25CU_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return P25CU_OK;
+}
+extern "C" uint64_t p25cu_launch_count(const p25cu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int p25cu_device_baseband(p25cu_ctx* ctx, const float** ptr, size_t* row_stride, size_t* n_out) {
+    if (!ctx || !ptr) return P25CU_ERR_ARG;
+    *ptr = ctx->d_bb + P25CU_BB_HIST;
+    if (row_stride) *row_stride = ctx->row_stride;
+    if (n_out) *n_out = ctx->last_n_out;
+    return P25CU_OK;
+}
+
+// ---------------------------------------------------------------- FEC unit entry point
+extern "C" int p25cu_fec_selftest(p25cu_ctx* ctx, int kind, void* words, size_t count, int n, int k, void* out_data,
+                                  int32_t* out_nerr) {
+    if (!ctx || !words || !out_nerr || kind < 0 || kind > 9) return P25CU_ERR_ARG;
+    if (kind == 7 && (n < 1 || n > 36 || k < 1 || k >= n || ((n - k) != 8 && (n - k) != 12 && (n - k) != 16)))
+        return fail_arg(ctx, "rs selftest: unsupported (n, k)");
+    if (kind != 7 && !out_data) return P25CU_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    size_t in_b, out_b;
+    switch (kind) {
+        case 0: in_b = 8; out_b = 4; break;
+        case 7: in_b = (size_t)n; out_b = 0; break;
+        case 8: in_b = 98; out_b = 12; break;
+        case 9: in_b = 72; out_b = 60; break;
+        default: in_b = 4; out_b = 4; break;
+    }
+    void *d_in = nullptr, *d_out = nullptr;
+    int32_t* d_nerr = nullptr;
+    int rc = P25CU_OK;
+    cudaError_t e;
+#define CKF(call) if ((e = (call)) != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "%s: %s", #call, cudaGetErrorString(e)); rc = P25CU_ERR_CUDA; goto done; }
+    if (count == 0) return P25CU_OK;
+    CKF(cudaMalloc(&d_in, count * in_b));
+    CKF(cudaMalloc(&d_nerr, count * sizeof(int32_t)));
+    if (out_b) CKF(cudaMalloc(&d_out, count * out_b));
+    CKF(cudaMemcpyAsync(d_in, words, count * in_b, cudaMemcpyHostToDevice, ctx->stream));
+    CKF(p25cu_launch_fec_selftest(ctx->d_tables, kind, d_in, count, n, k, d_out, d_nerr, ctx->stream));
+    ctx->launches++;
+    if (kind == 7) CKF(cudaMemcpyAsync(words, d_in, count * in_b, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_b) CKF(cudaMemcpyAsync(out_data, d_out, count * out_b, cudaMemcpyDeviceToHost, ctx->stream));
+    CKF(cudaMemcpyAsync(out_nerr, d_nerr, count * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CKF(cudaStreamSynchronize(ctx->stream));
+done:
+    cudaFree(d_in);
+    cudaFree(d_out);
+    cudaFree(d_nerr);
+    return rc;
+}

@@ -1,0 +1,209 @@
+"""Host-side mirror of the reference's hot-path interfaces over the C ABI.
+
+  DemodTask        <-> reference src/demod.rs:25-119   (one run-loop iteration per call)
+  MessageReceiver  <-> p25::message::receiver::MessageReceiver as used at src/recv.rs:81,:207,:136
+  ReplayReceiver   <-> reference src/replay.rs:11-57
+  power_dbm        <-> reference src/demod.rs:123-134 (computed inside DemodTask.run_chunk)
+
+Every class is batched over `n_streams` independent streams that live on one GPU.  All
+arithmetic happens in libp25cu.so (CUDA, sm_100a); this module only moves pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import EVENT_DTYPE, FMT_CF32_IQ, FMT_U8_IQ, P25Error
+
+# MessageEvent variants (reference src/recv.rs:214-233)
+EV_ERROR, EV_NID, EV_VOICE_HEADER, EV_LINK_CONTROL, EV_CRYPTO_CONTROL, EV_LSD, EV_VOICE_FRAME, EV_TSBK, EV_VOICE_TERM = range(9)
+EVENT_NAMES = ["Error", "PacketNID", "VoiceHeader", "LinkControl", "CryptoControl", "LowSpeedDataFragment",
+               "VoiceFrame", "TrunkingControl", "VoiceTerm"]
+STATS_FAMILIES = ["bch", "cyclic", "golayStd", "golayExt", "golayShort", "hammingStd", "hammingShort",
+                  "rsShort", "rsMed", "rsLong", "viterbiDibit", "viterbiTribit"]   # reference src/hub.rs:557-572
+
+BUF_BYTES = 32768            # reference src/consts.rs:6
+BUF_SAMPLES = BUF_BYTES // 2  # reference src/consts.rs:8
+
+
+def _as_ptr(x):
+    """numpy array, torch tensor (host or device) or int address -> (void*, on_device)."""
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data_as(C.c_void_p), False
+    if hasattr(x, "data_ptr"):  # torch.Tensor without importing torch here
+        return C.c_void_p(x.data_ptr()), bool(x.is_cuda)
+    raise TypeError(f"unsupported buffer type {type(x)}")
+
+
+class Context:
+    """One p25cu_ctx: n_streams streams on one GPU."""
+
+    def __init__(self, n_streams: int, fmt: int = FMT_U8_IQ, decimation: int = 5, max_chunk_samples: int = BUF_SAMPLES,
+                 max_baseband: int = 0, device: int = 0):
+        self._L = _lib.lib()
+        cfg = _lib.Config(device, n_streams, fmt, decimation, max_chunk_samples, max_baseband, _lib.ABI_VERSION, 0)
+        h = C.c_void_p()
+        rc = self._L.p25cu_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise P25Error(rc, self._L.p25cu_last_error(None).decode())
+        self._h = h
+        self.n_streams, self.fmt, self.decimation = n_streams, fmt, decimation
+        self.max_chunk_samples = max_chunk_samples
+        self._a_abs = 0  # input samples consumed per stream (decimator phase bookkeeping)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.p25cu_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _ck(self, rc: int, ok=(0,)):
+        if rc not in ok:
+            raise P25Error(rc, self._L.p25cu_last_error(self._h).decode())
+        return rc
+
+    # ---- Surface 1
+    def demod(self, iq, n_in_per_stream: int, want_baseband: bool = True, want_power: bool = False):
+        """p25cu_demod.  iq: numpy array (host) or torch tensor (host or cuda), [S][n] samples of the
+        context's format.  Returns (baseband [S][n_out] or None, n_out, power_dbm [S] or None)."""
+        ptr, on_dev = _as_ptr(iq)
+        n = int(n_in_per_stream)
+        n_expect = (self._a_abs + n) // self.decimation - self._a_abs // self.decimation
+        bb = np.empty((self.n_streams, n_expect), dtype=np.float32) if want_baseband else None
+        pw = np.empty(self.n_streams, dtype=np.float32) if want_power else None
+        n_out = C.c_size_t(0)
+        self._ck(self._L.p25cu_demod(self._h, ptr, n, int(on_dev), bb.ctypes.data_as(C.c_void_p) if want_baseband else None,
+                                     C.byref(n_out), pw.ctypes.data_as(C.c_void_p) if want_power else None))
+        self._a_abs += n
+        assert n_out.value == n_expect
+        return bb, n_out.value, pw
+
+    # ---- Surface 2
+    def decode(self, baseband: np.ndarray | None = None):
+        if baseband is None:
+            self._ck(self._L.p25cu_decode(self._h, None, 0))
+            return
+        bb = np.ascontiguousarray(baseband, dtype=np.float32).reshape(self.n_streams, -1)
+        self._ck(self._L.p25cu_decode(self._h, bb.ctypes.data_as(C.c_void_p), bb.shape[1]))
+
+    def process(self, iq, n_in_per_stream: int):
+        ptr, on_dev = _as_ptr(iq)
+        self._ck(self._L.p25cu_process(self._h, ptr, n_in_per_stream, int(on_dev)))
+        self._a_abs += int(n_in_per_stream)
+
+    def pending(self) -> int:
+        n = C.c_size_t(0)
+        self._ck(self._L.p25cu_pending(self._h, C.byref(n)))
+        return n.value
+
+    def poll(self, cap: int | None = None) -> np.ndarray:
+        if cap is None:
+            cap = self.pending()
+        ev = np.zeros(max(cap, 1), dtype=EVENT_DTYPE)
+        n = C.c_size_t(0)
+        self._ck(self._L.p25cu_poll(self._h, ev.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+        return ev[: n.value]
+
+    def resync(self, stream: int):
+        self._ck(self._L.p25cu_resync(self._h, stream))
+
+    def stats(self, stream: int, clear: bool = False) -> np.ndarray:
+        st = _lib.Stats()
+        self._ck(self._L.p25cu_get_stats(self._h, stream, C.byref(st), int(clear)))
+        return np.ctypeslib.as_array(st.code).astype(np.uint64).reshape(12, 4).copy()
+
+    def sync(self):
+        self._ck(self._L.p25cu_sync(self._h))
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(self._L.p25cu_cuda_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.p25cu_launch_count(self._h))
+
+    def fec_selftest(self, kind: int, words: np.ndarray, n: int = 0, k: int = 0):
+        words = np.ascontiguousarray(words)
+        if kind == 0:
+            count, out = words.size, np.zeros(words.size, dtype=np.uint32)
+        elif kind == 7:
+            count, out = words.size // n, None
+        elif kind == 8:
+            count = words.size // 98
+            out = np.zeros((count, 12), dtype=np.uint8)
+        elif kind == 9:
+            count = words.size // 72
+            out = np.zeros((count, 15), dtype=np.uint32)
+        else:
+            count, out = words.size, np.zeros(words.size, dtype=np.uint32)
+        nerr = np.zeros(count, dtype=np.int32)
+        self._ck(self._L.p25cu_fec_selftest(self._h, kind, words.ctypes.data_as(C.c_void_p), count, n, k,
+                                            out.ctypes.data_as(C.c_void_p) if out is not None else None,
+                                            nerr.ctypes.data_as(C.c_void_p)))
+        return (words if kind == 7 else out), nerr
+
+
+class DemodTask:
+    """Batched DemodTask (reference src/demod.rs:25-119): IQ chunk in, 48 kHz baseband chunk out."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self._notifier = 0  # Throttler::new(4), reference src/demod.rs:67
+
+    def run_chunk(self, iq, n_in_per_stream: int | None = None):
+        """One loop iteration (src/demod.rs:70-117).  Returns (baseband [S][n_out], power_dbm or None);
+        like the reference the signal power is reported on every 4th chunk only (src/demod.rs:95-101)."""
+        want_power = self._notifier == 0
+        self._notifier = (self._notifier + 1) % 4
+        if n_in_per_stream is None:
+            n_in_per_stream = iq.size // self.ctx.n_streams // (2 if self.ctx.fmt == FMT_U8_IQ else 1)
+        bb, _, pw = self.ctx.demod(iq, n_in_per_stream, want_baseband=True, want_power=want_power)
+        return bb, pw
+
+
+class MessageReceiver:
+    """Batched p25 MessageReceiver: feed() takes [S][n] baseband samples and returns the events of all
+    streams ordered by (stream, sample); per stream this is the order the reference's feed() yields."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    def feed(self, samples: np.ndarray) -> np.ndarray:
+        self.ctx.decode(samples)
+        return self.ctx.poll()
+
+    def resync(self, stream: int):
+        self.ctx.resync(stream)
+
+
+class ReplayReceiver:
+    """reference src/replay.rs:11-57 for one or more f32le/48 kHz/mono baseband recordings."""
+
+    READ_BYTES = 32768  # src/replay.rs:27
+
+    def __init__(self, n_streams: int = 1, device: int = 0, on_voice_frame=None):
+        self.ctx = Context(n_streams, fmt=FMT_U8_IQ, decimation=5, max_chunk_samples=BUF_SAMPLES,
+                           max_baseband=self.READ_BYTES // 4, device=device)
+        self.msg = MessageReceiver(self.ctx)
+        self.on_voice_frame = on_voice_frame
+        self.events: list[np.ndarray] = []
+
+    def replay(self, streams) -> np.ndarray:
+        """streams: list of binary file objects (one per stream).  Unlike src/replay.rs:36 a short final
+        read is fed at its true length (the reference re-feeds the stale tail of its buffer)."""
+        while True:
+            blocks = [f.read(self.READ_BYTES) for f in streams]
+            n = min(len(b) for b in blocks) // 4
+            if n == 0:
+                break
+            chunk = np.stack([np.frombuffer(b[: 4 * n], dtype="<f4") for b in blocks])
+            ev = self.msg.feed(chunk)
+            if self.on_voice_frame is not None:
+                for e in ev[ev["kind"] == EV_VOICE_FRAME]:
+                    self.on_voice_frame(e)
+            self.events.append(ev)
+        return np.concatenate(self.events) if self.events else np.zeros(0, dtype=EVENT_DTYPE)
