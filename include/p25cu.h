@@ -55,7 +55,8 @@ typedef struct {
     uint64_t max_baseband;      /* largest n_per_stream for p25cu_decode of caller-provided baseband;
                                    0 = derive from max_chunk_samples / decimation */
     uint32_t abi_version;       /* P25CU_ABI_VERSION */
-    uint32_t flags;             /* reserved, 0 */
+    uint32_t event_slots;       /* event slots per stream between two p25cu_poll calls; 0 = sized for one
+                                   chunk (max baseband / 200 + 16) */
 } p25cu_config;
 
 /* MessageEvent variants as matched at reference src/recv.rs:214-233. */

@@ -30,7 +30,7 @@ EXPORTS = ["p25cu_create", "p25cu_destroy", "p25cu_last_error", "p25cu_demod", "
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("n_streams", C.c_uint32), ("format", C.c_int32), ("decimation", C.c_int32),
                 ("max_chunk_samples", C.c_uint64), ("max_baseband", C.c_uint64), ("abi_version", C.c_uint32),
-                ("flags", C.c_uint32)]
+                ("event_slots", C.c_uint32)]
 
 
 class Stats(C.Structure):

@@ -67,25 +67,57 @@ __device__ __forceinline__ float2 load_logical(const DdcParams& p, const float2*
     return cf_from_u8(__ldcs((const uchar2*)chunk + i));
 }
 
+// Stage logical samples [l0, l0 + XN) into sm.xs.  Global loads are 16 bytes wide and aligned to the
+// *source* (2 cf32 samples or 8 u8 samples per load); each sample is then stored to its own slot, so
+// any decimator phase / chunk parity takes the vector path as long as the rows themselves are aligned.
 template <bool FRONT, int FMT>
 __device__ __forceinline__ void stage_block(Smem<FRONT>& sm, const DdcParams& p, const float2* tail, const void* chunk,
                                             long long l0) {
     using C = Cfg<FRONT>;
-    if (FMT == P25CU_FMT_CF32_IQ && p.aligned16) {
-        // 16-byte path: two samples per load; pairs never straddle tail/chunk or the chunk end
-        for (int i = 2 * threadIdx.x; i < C::XN; i += 2 * C::NT) {
-            const long long l = l0 + i;
-            float4 v;
-            if (l < (long long)p.ht) {
-                v = *(const float4*)(tail + l);
-            } else {
-                const long long j = l - p.ht;
-                v = j < (long long)p.n ? __ldcs((const float4*)((const float2*)chunk + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long ht = (long long)p.ht;
+    const int tid = threadIdx.x;
+    // part 1: samples that still come from the previous chunk's tail (cf32, HT is even)
+    const long long t_end = l0 + C::XN < ht ? l0 + C::XN : ht;
+    if (l0 < t_end) {
+        for (long long l = (l0 & ~1LL) + 2 * tid; l < t_end; l += 2 * C::NT) {
+            const float4 v = *(const float4*)(tail + l);
+            const long long i = l - l0;
+            if (i >= 0) sm.xs[i] = make_float2(v.x, v.y);
+            if (i + 1 < C::XN && l + 1 < t_end) sm.xs[i + 1] = make_float2(v.z, v.w);
+        }
+    }
+    // part 2: samples of this chunk (zeros past its end)
+    const long long c_beg = (l0 > ht ? l0 : ht) - ht, c_end = l0 + C::XN - ht;
+    if (c_end <= c_beg) return;
+    const long long base = ht - l0;   // xs index = chunk index + base
+    const long long n = (long long)p.n;
+    if (p.aligned16) {
+        if (FMT == P25CU_FMT_CF32_IQ) {
+            for (long long g = (c_beg & ~1LL) + 2 * tid; g < c_end; g += 2 * C::NT) {
+                const float4 v = g < n ? __ldcs((const float4*)((const float2*)chunk + g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g >= c_beg) sm.xs[g + base] = make_float2(v.x, v.y);
+                if (g + 1 < c_end) sm.xs[g + 1 + base] = make_float2(v.z, v.w);
             }
-            *(float4*)(&sm.xs[i]) = v;
+        } else {
+            for (long long g = (c_beg & ~7LL) + 8 * tid; g < c_end; g += 8 * C::NT) {
+                const uint4 v = g < n ? __ldcs((const uint4*)((const uchar2*)chunk + g)) : make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu);
+                const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const long long jj = g + e;
+                    if (jj >= c_beg && jj < c_end) {
+                        const unsigned b = w[e >> 1] >> (16 * (e & 1));
+                        sm.xs[jj + base] = jj < n ? make_float2(c_iq_lut[b & 0xFF], c_iq_lut[(b >> 8) & 0xFF]) : make_float2(0.f, 0.f);
+                    }
+                }
+            }
         }
     } else {
-        for (int i = threadIdx.x; i < C::XN; i += C::NT) sm.xs[i] = load_logical<FMT>(p, tail, chunk, l0 + i);
+        for (long long jj = c_beg + tid; jj < c_end; jj += C::NT) {
+            float2 v = make_float2(0.f, 0.f);
+            if (jj < n) v = (FMT == P25CU_FMT_CF32_IQ) ? __ldcs((const float2*)chunk + jj) : cf_from_u8(__ldcs((const uchar2*)chunk + jj));
+            sm.xs[jj + base] = v;
+        }
     }
 }
 

@@ -487,48 +487,36 @@ cudaError_t p25cu_launch_compact(const WalkState* states, const p25cu_event* slo
 }
 
 // ---------------------------------------------------------------- FEC unit kernels (parity tests)
-__global__ void p25_fec_selftest_kernel(const P25DevTables* tables, int kind, void* words, size_t count, int n, int k,
-                                        void* out_data, int32_t* out_nerr) {
+// One kernel per decoder (template on KIND) so that each has its own stack frame.
+template <int KIND>
+__global__ void p25_fec_selftest_kernel(const P25DevTables* tables, void* words, size_t count, int n, int k, void* out_data,
+                                        int32_t* out_nerr) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const P25DevTables& T = *tables;
-    unsigned d = 0;
-    switch (kind) {
-        case 0: out_nerr[i] = p25_bch_decode(T, ((const unsigned long long*)words)[i], &d); ((unsigned*)out_data)[i] = d; break;
-        case 1: out_nerr[i] = p25_golay23_decode(T, ((const unsigned*)words)[i], &d); ((unsigned*)out_data)[i] = d; break;
-        case 2: out_nerr[i] = p25_golay24_decode(T, ((const unsigned*)words)[i], &d); ((unsigned*)out_data)[i] = d; break;
-        case 3: out_nerr[i] = p25_golay18_decode(T, ((const unsigned*)words)[i], &d); ((unsigned*)out_data)[i] = d; break;
-        case 4: out_nerr[i] = p25_hamming15_decode(T, ((const unsigned*)words)[i], &d); ((unsigned*)out_data)[i] = d; break;
-        case 5: out_nerr[i] = p25_hamming10_decode(T, ((const unsigned*)words)[i], &d); ((unsigned*)out_data)[i] = d; break;
-        case 6: out_nerr[i] = p25_cyclic16_decode(T, ((const unsigned*)words)[i], &d); ((unsigned*)out_data)[i] = d; break;
-        case 7: {
-            unsigned char sym[36];
-            unsigned char* w = (unsigned char*)words + i * n;
-            for (int j = 0; j < n; j++) sym[j] = w[j];
-            out_nerr[i] = p25_rs_decode(T, sym, n, k);
-            for (int j = 0; j < n; j++) w[j] = sym[j];
-            break;
-        }
-        case 8: {
-            unsigned char in[98], out[12];
-            const unsigned char* w = (const unsigned char*)words + i * 98;
-            for (int j = 0; j < 98; j++) in[j] = w[j];
-            for (int j = 0; j < 12; j++) out[j] = 0;
-            out_nerr[i] = p25_trellis_half_decode(T, in, out);
-            for (int j = 0; j < 12; j++) ((unsigned char*)out_data)[i * 12 + j] = out[j];
-            break;
-        }
-        case 9: {
-            unsigned char in[72];
-            unsigned pl[15];
-            const unsigned char* w = (const unsigned char*)words + i * 72;
-            for (int j = 0; j < 72; j++) in[j] = w[j];
-            p25_imbe_decode(T, in, pl, pl + 8);
-            for (int j = 0; j < 15; j++) ((unsigned*)out_data)[i * 15 + j] = pl[j];
-            out_nerr[i] = 0;
-            break;
-        }
-        default: break;
+    if constexpr (KIND <= 6) {
+        unsigned d = 0;
+        int r;
+        if constexpr (KIND == 0) r = p25_bch_decode(T, ((const unsigned long long*)words)[i], &d);
+        else if constexpr (KIND == 1) r = p25_golay23_decode(T, ((const unsigned*)words)[i], &d);
+        else if constexpr (KIND == 2) r = p25_golay24_decode(T, ((const unsigned*)words)[i], &d);
+        else if constexpr (KIND == 3) r = p25_golay18_decode(T, ((const unsigned*)words)[i], &d);
+        else if constexpr (KIND == 4) r = p25_hamming15_decode(T, ((const unsigned*)words)[i], &d);
+        else if constexpr (KIND == 5) r = p25_hamming10_decode(T, ((const unsigned*)words)[i], &d);
+        else r = p25_cyclic16_decode(T, ((const unsigned*)words)[i], &d);
+        out_nerr[i] = r;
+        ((unsigned*)out_data)[i] = d;
+    } else if constexpr (KIND == 7) {
+        out_nerr[i] = p25_rs_decode(T, (unsigned char*)words + i * n, n, k);  // in place, in global memory
+    } else if constexpr (KIND == 8) {
+        unsigned char out[12];
+        out_nerr[i] = p25_trellis_half_decode(T, (const unsigned char*)words + i * 98, out);
+        for (int j = 0; j < 12; j++) ((unsigned char*)out_data)[i * 12 + j] = out_nerr[i] < 0 ? 0 : out[j];
+    } else {
+        unsigned pl[15];
+        p25_imbe_decode(T, (const unsigned char*)words + i * 72, pl, pl + 8);
+        for (int j = 0; j < 15; j++) ((unsigned*)out_data)[i * 15 + j] = pl[j];
+        out_nerr[i] = 0;
     }
 }
 
@@ -536,6 +524,12 @@ cudaError_t p25cu_launch_fec_selftest(const P25DevTables* tables, int kind, void
                                       void* out_data, int32_t* out_nerr, cudaStream_t st) {
     const unsigned blocks = (unsigned)((count + 127) / 128);
     if (blocks == 0) return cudaSuccess;
-    p25_fec_selftest_kernel<<<blocks, 128, 0, st>>>(tables, kind, words, count, n, k, out_data, out_nerr);
+#define P25_ST_CASE(K) case K: p25_fec_selftest_kernel<K><<<blocks, 128, 0, st>>>(tables, words, count, n, k, out_data, out_nerr); break;
+    switch (kind) {
+        P25_ST_CASE(0) P25_ST_CASE(1) P25_ST_CASE(2) P25_ST_CASE(3) P25_ST_CASE(4)
+        P25_ST_CASE(5) P25_ST_CASE(6) P25_ST_CASE(7) P25_ST_CASE(8) P25_ST_CASE(9)
+        default: return cudaErrorInvalidValue;
+    }
+#undef P25_ST_CASE
     return cudaGetLastError();
 }

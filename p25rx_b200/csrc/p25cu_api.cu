@@ -100,7 +100,7 @@ static int create_impl(p25cu_ctx* ctx) {
     ctx->max_out = cfg.max_chunk_samples / cfg.decimation + 1;
     if (cfg.max_baseband > ctx->max_out) ctx->max_out = cfg.max_baseband;
     ctx->row_stride = (P25CU_BB_HIST + ctx->max_out + 3) & ~(size_t)3;
-    ctx->ev_cap = (unsigned)(ctx->max_out / 200 + 16);
+    ctx->ev_cap = cfg.event_slots ? cfg.event_slots : (unsigned)(ctx->max_out / 200 + 16);
 
     CK(cudaMalloc(&ctx->d_tail[0], S * ctx->ht * sizeof(float2)));
     CK(cudaMalloc(&ctx->d_tail[1], S * ctx->ht * sizeof(float2)));
@@ -199,7 +199,8 @@ extern "C" int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_d
     p.n_out = (unsigned)((ctx->a_abs + n) / D - p.m0);
     p.n_streams = (unsigned)S;
     p.ht = ctx->ht;
-    p.aligned16 = ((ctx->a_abs & 1) == 0) && ((n & 1) == 0) && (((uintptr_t)d_in & 15) == 0);
+    // every stream's row must start 16-byte aligned: 2 cf32 or 8 u8 samples per 16-byte load
+    p.aligned16 = ((n % (ctx->cfg.format == P25CU_FMT_U8_IQ ? 8 : 2)) == 0) && (((uintptr_t)d_in & 15) == 0);
     {
         const unsigned mb = p25cu_ddc_block_out(D);
         const unsigned iters = (p.n_out + mb - 1) / mb;

@@ -68,7 +68,7 @@ struct DdcParams {
     unsigned seg_out;             // outputs per segment (multiple of the per-iteration block)
     unsigned n_seg;               // segments per stream
     unsigned ht;                  // tail length in samples
-    int aligned16;                // chunk rows start 16-byte aligned and a0 is even
+    int aligned16;                // every chunk row starts 16-byte aligned and holds whole 16-byte groups
 };
 
 // kernels (defined in ddc_fm.cu / decode_walk.cu)

@@ -41,9 +41,9 @@ class Context:
     """One p25cu_ctx: n_streams streams on one GPU."""
 
     def __init__(self, n_streams: int, fmt: int = FMT_U8_IQ, decimation: int = 5, max_chunk_samples: int = BUF_SAMPLES,
-                 max_baseband: int = 0, device: int = 0):
+                 max_baseband: int = 0, device: int = 0, event_slots: int = 0):
         self._L = _lib.lib()
-        cfg = _lib.Config(device, n_streams, fmt, decimation, max_chunk_samples, max_baseband, _lib.ABI_VERSION, 0)
+        cfg = _lib.Config(device, n_streams, fmt, decimation, max_chunk_samples, max_baseband, _lib.ABI_VERSION, event_slots)
         h = C.c_void_p()
         rc = self._L.p25cu_create(C.byref(cfg), C.byref(h))
         if rc != 0:

@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA library, called through its C ABI, against the CPU oracle.
+
+Bar (north star): decoded NIDs / TSBK / LC / voice frames and their sample indices bit-exact;
+FEC decoders bit-exact; discriminator / boxcar samples within 1e-4 absolute of the oracle
+(full scale is +-4.8, so 2e-5 of full scale)."""
+import numpy as np
+import p25_spec as S
+import pytest
+from tools import p25tx as tx
+from util import check_against_truth, events_key, oracle_events
+
+pytestmark = pytest.mark.gpu
+BB_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def p25():
+    import p25rx_b200
+    return p25rx_b200
+
+
+def _streams_baseband(kind: str, n: int, length: int | None = None):
+    rows, truth = [], []
+    for s in range(n):
+        st = tx.control_channel(100 + s, 3, lead_idle=20 + 7 * s) if kind == "control" else tx.traffic_channel(200 + s, 1, lead_idle=20 + 5 * s)
+        bb, _ = tx.baseband_48k(st.dibits, snr_db=22 if s % 2 else None, dc=0.01 * (s % 3), seed=s, timing_offset=(s * 1.7) % 10)
+        rows.append(bb)
+        truth.append(tx.expected_events(st))
+    length = length or min(len(r) for r in rows)
+    return np.stack([r[:length] for r in rows]), truth
+
+
+# ------------------------------------------------------------------ FEC decoders
+def test_fec_decoders_bit_exact(p25, oracle):
+    import ctypes as C
+    O = oracle.lib()
+    ctx = p25.Context(1, max_chunk_samples=1024)
+    rng = np.random.default_rng(0)
+    n = 20000
+    # BCH: codewords with 0..15 errors plus random words
+    words = np.zeros(n, dtype=np.uint64)
+    for i in range(n):
+        w = S.bch_encode(int(rng.integers(0, 65536)))
+        for p in rng.choice(63, int(rng.integers(0, 16)), replace=False):
+            w ^= 1 << int(p)
+        words[i] = w if i % 5 else int(rng.integers(0, 1 << 63))
+    data, nerr = ctx.fec_selftest(0, words)
+    for i in range(0, n, 7):
+        od, on = C.c_uint16(), C.c_int()
+        ok = O.p25o_bch_decode(int(words[i]), C.byref(od), C.byref(on))
+        assert (nerr[i] >= 0) == bool(ok)
+        if ok:
+            assert nerr[i] == on.value and data[i] == od.value
+    # short codes: random words (every syndrome class is exercised)
+    for kind, name, bits in ((1, "golay23", 23), (2, "golay24", 24), (3, "golay18", 18), (4, "hamming15", 15),
+                             (5, "hamming10", 10), (6, "cyclic16", 16)):
+        w = rng.integers(0, 1 << bits, n).astype(np.uint32)
+        data, nerr = ctx.fec_selftest(kind, w)
+        fo = getattr(O, f"p25o_{name}_decode")
+        for i in range(0, n, 5):
+            a = C.c_uint32()
+            assert fo(int(w[i]), C.byref(a)) == nerr[i] and a.value == data[i], (name, i)
+    # Reed-Solomon
+    for (nn, kk) in (S.RS_SHORT, S.RS_MED, S.RS_LONG):
+        t = (nn - kk) // 2
+        blocks = np.zeros((4000, nn), dtype=np.uint8)
+        for i in range(len(blocks)):
+            cw = S.rs_encode([int(x) for x in rng.integers(0, 64, kk)], nn, kk)
+            for p in rng.choice(nn, int(rng.integers(0, t + 3)), replace=False):
+                cw[int(p)] ^= int(rng.integers(1, 64))
+            blocks[i] = cw if i % 4 else rng.integers(0, 64, nn)
+        ref = blocks.copy()
+        fixed, nerr = ctx.fec_selftest(7, blocks.copy(), nn, kk)
+        fixed = fixed.reshape(-1, nn)
+        for i in range(len(ref)):
+            r = O.p25o_rs_decode(ref[i].ctypes.data_as(C.c_void_p), nn, kk)
+            assert r == nerr[i] and (ref[i] == fixed[i]).all()
+    # trellis + IMBE
+    blocks = np.zeros((4000, 98), dtype=np.uint8)
+    for i in range(len(blocks)):
+        d = S.tsbk_block_dibits(rng.integers(0, 256, 12).astype(np.uint8).tobytes()).copy()
+        for p in rng.choice(196, int(rng.integers(0, 20)), replace=False):
+            d[int(p) // 2] ^= 2 >> (int(p) & 1)
+        blocks[i] = d if i % 5 else rng.integers(0, 4, 98)
+    out, nerr = ctx.fec_selftest(8, blocks)
+    for i in range(len(blocks)):
+        o = np.zeros(12, np.uint8)
+        r = O.p25o_trellis_half_decode(blocks[i].ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
+        assert r == nerr[i] and (r < 0 or (o == out[i]).all())
+    blocks = np.zeros((4000, 72), dtype=np.uint8)
+    for i in range(len(blocks)):
+        d = S.imbe_encode([int(rng.integers(0, 1 << b)) for b in S.IMBE_U_BITS]).copy()
+        for p in rng.choice(144, int(rng.integers(0, 14)), replace=False):
+            d[int(p) // 2] ^= 2 >> (int(p) & 1)
+        blocks[i] = d
+    out, _ = ctx.fec_selftest(9, blocks)
+    for i in range(len(blocks)):
+        c, e = np.zeros(8, np.uint32), np.zeros(7, np.uint32)
+        O.p25o_imbe_decode(blocks[i].ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p))
+        assert (out[i, :8] == c).all() and (out[i, 8:] == e).all()
+    ctx.close()
+
+
+# ------------------------------------------------------------------ decode (Surface 2)
+@pytest.mark.parametrize("kind", ["control", "traffic"])
+@pytest.mark.parametrize("chunk", [None, 3277, 8192, 1000])
+def test_decode_bit_exact(p25, oracle, kind, chunk):
+    bb, truth = _streams_baseband(kind, 9)
+    ref, ref_stats = oracle_events(oracle, bb)
+    ctx = p25.Context(len(bb), max_chunk_samples=1024, max_baseband=bb.shape[1])
+    rx = p25.MessageReceiver(ctx)
+    if chunk is None:
+        ev = rx.feed(bb)
+    else:
+        ev = np.concatenate([rx.feed(bb[:, i:i + chunk]) for i in range(0, bb.shape[1], chunk)])
+        ev = ev[np.lexsort((ev["sample"], ev["stream"]))]
+    assert events_key(ev) == events_key(ref)
+    for s in range(len(bb)):
+        assert (ctx.stats(s) == ref_stats[s]).all(), s
+    check_against_truth(ev, truth[0][: np.count_nonzero(ev["stream"] == 0)], 0)
+    ctx.close()
+
+
+def test_decode_noise_and_garbage(p25, oracle):
+    """Low SNR, noise-only and constant streams: whatever the oracle decides, the GPU decides."""
+    rng = np.random.default_rng(3)
+    rows = []
+    for s in range(12):
+        st = tx.traffic_channel(300 + s, 1) if s % 2 else tx.control_channel(300 + s, 4)
+        bb, _ = tx.baseband_48k(st.dibits, snr_db=[4, 6, 8, 10, 12, 15][s % 6], seed=s, dc=0.02)
+        rows.append(bb)
+    n = min(len(r) for r in rows)
+    rows = [r[:n] for r in rows]
+    rows.append(rng.normal(0, 0.6, n).astype(np.float32))
+    rows.append(np.zeros(n, dtype=np.float32))
+    rows.append(np.full(n, 0.3, dtype=np.float32))
+    bb = np.stack(rows)
+    ref, ref_stats = oracle_events(oracle, bb)
+    ctx = p25.Context(len(bb), max_chunk_samples=1024, max_baseband=bb.shape[1])
+    ev = p25.MessageReceiver(ctx).feed(bb)
+    assert events_key(ev) == events_key(ref)
+    assert np.count_nonzero(ev["kind"] == 0) > 0          # the error paths were exercised
+    for s in range(len(bb)):
+        assert (ctx.stats(s) == ref_stats[s]).all()
+    ctx.close()
+
+
+def test_resync_and_stats_clear(p25, oracle):
+    bb, _ = _streams_baseband("control", 3)
+    cut = 2000
+    ctx = p25.Context(3, max_chunk_samples=1024, max_baseband=bb.shape[1])
+    rx = p25.MessageReceiver(ctx)
+    ev1 = rx.feed(bb[:, :cut])
+    rx.resync(1)
+    ev2 = rx.feed(bb[:, cut:])
+    ref = []
+    for s in range(3):
+        o = oracle.MessageReceiver(stream=s)
+        ref.append(o.feed(bb[s, :cut]))
+        if s == 1:
+            o.resync()
+        ref.append(o.feed(bb[s, cut:]))
+    ref = np.concatenate(ref)
+    got = np.concatenate([ev1, ev2])
+    got = got[np.lexsort((got["sample"], got["stream"]))]
+    ref = ref[np.lexsort((ref["sample"], ref["stream"]))]
+    assert events_key(got) == events_key(ref)
+    assert ctx.stats(0, clear=True)[0, 0] > 0 and ctx.stats(0)[:, [0, 1, 3]].sum() == 0
+    ctx.close()
+
+
+# ------------------------------------------------------------------ demod (Surface 1)
+@pytest.mark.parametrize("fmt,dec", [("cf32", 5), ("u8", 5), ("cf32", 50), ("u8", 50)])
+@pytest.mark.parametrize("chunk", [16384, 30000, 4999])
+def test_demod_within_tolerance(p25, oracle, fmt, dec, chunk):
+    fs = 240_000 * (dec // 5)
+    S_ = 5
+    rows = []
+    for s in range(S_):
+        st = tx.control_channel(400 + s, 2)
+        rows.append(tx.modulate_iq(st.dibits, fs, snr_db=25, cfo_hz=50.0 * s, seed=s)[: 4 * chunk + 123])
+    n = min(len(r) for r in rows)
+    iq = np.stack([r[:n] for r in rows])
+    if fmt == "u8":
+        data = np.stack([tx.iq_to_u8(r) for r in iq])
+        ofmt, gfmt = oracle.FMT_U8, p25.FMT_U8_IQ
+    else:
+        data, ofmt, gfmt = iq, oracle.FMT_CF32, p25.FMT_CF32_IQ
+    ctx = p25.Context(S_, fmt=gfmt, decimation=dec, max_chunk_samples=chunk)
+    chains = [oracle.DemodChain(ofmt, dec == 50) for _ in range(S_)]
+    per = 2 if fmt == "u8" else 1
+    worst = 0.0
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        part = np.ascontiguousarray(data[:, per * i: per * (i + m)])
+        bb, n_out, pw = ctx.demod(part, m, want_power=True)
+        for s in range(S_):
+            ref, pref = chains[s].feed(part[s], want_power=True)
+            assert len(ref) == n_out
+            if n_out:
+                worst = max(worst, float(np.max(np.abs(bb[s] - ref))))
+                assert abs(pw[s] - pref) < 1e-2
+    assert worst < BB_TOL, worst
+    ctx.close()
+
+
+def test_demod_odd_chunks_and_device_input(p25, oracle):
+    """Odd chunk lengths force the unaligned load path; a torch CUDA tensor is used without a host copy."""
+    import torch
+    st = tx.control_channel(500, 3)
+    iq = tx.modulate_iq(st.dibits, 240_000, snr_db=25, seed=1)[:40001]
+    assert len(iq) == 40001
+    ctx = p25.Context(2, fmt=p25.FMT_CF32_IQ, decimation=5, max_chunk_samples=20000)
+    chains = [oracle.DemodChain(oracle.FMT_CF32, False) for _ in range(2)]
+    pos = 0
+    for m in (777, 12345, 20000, 6879):
+        part = np.ascontiguousarray(np.stack([iq[pos:pos + m], iq[pos:pos + m][::-1]]))
+        dev = torch.from_numpy(part.view(np.float32)).cuda()
+        bb, n_out, _ = ctx.demod(dev, m)
+        for s in range(2):
+            ref = chains[s].feed(part[s])
+            assert len(ref) == n_out and np.max(np.abs(bb[s] - ref)) < BB_TOL
+        pos += m
+    ctx.close()
+
+
+# ------------------------------------------------------------------ end to end (the hot path)
+@pytest.mark.parametrize("fmt,dec", [("cf32", 50), ("u8", 5), ("cf32", 5)])
+def test_process_iq_to_events(p25, oracle, fmt, dec):
+    fs = 240_000 * (dec // 5)
+    S_ = 6
+    rows, truth = [], []
+    for s in range(S_):
+        st = tx.control_channel(600 + s, 3) if s % 2 == 0 else tx.traffic_channel(600 + s, 1)
+        rows.append(tx.modulate_iq(st.dibits[: 2200], fs, snr_db=20, cfo_hz=-120.0 + 60 * s, timing_offset=1.3 * s, seed=s))
+        truth.append(tx.expected_events(st))
+    n = min(len(r) for r in rows)
+    iq = np.stack([r[:n] for r in rows])
+    if fmt == "u8":
+        data = np.stack([tx.iq_to_u8(r) for r in iq])
+        ofmt, gfmt = oracle.FMT_U8, p25.FMT_U8_IQ
+    else:
+        data, ofmt, gfmt = iq, oracle.FMT_CF32, p25.FMT_CF32_IQ
+    chunk = 16384 * (dec // 5)
+    ctx = p25.Context(S_, fmt=gfmt, decimation=dec, max_chunk_samples=chunk)
+    per = 2 if fmt == "u8" else 1
+    got = []
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        ctx.process(np.ascontiguousarray(data[:, per * i: per * (i + m)]), m)
+        got.append(ctx.poll())
+    got = np.concatenate(got)
+    got = got[np.lexsort((got["sample"], got["stream"]))]
+    ref = []
+    for s in range(S_):
+        bb = oracle.DemodChain(ofmt, dec == 50).feed(data[s])
+        ref.append(oracle.MessageReceiver(stream=s).feed(bb))
+    ref = np.concatenate(ref)
+    assert events_key(got) == events_key(ref)
+    assert len(got) > 40
+    ctx.close()
+
+
+def test_golden_fixtures(p25):
+    """Committed fixtures (tests/golden/make_golden.py): input baseband -> expected events."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "decode_golden.npz"))
+    bb, exp = g["baseband"].astype(np.float32), g["events"]
+    ctx = p25.Context(bb.shape[0], max_chunk_samples=1024, max_baseband=bb.shape[1])
+    ev = p25.MessageReceiver(ctx).feed(bb)
+    assert events_key(ev) == events_key(exp.view(p25.EVENT_DTYPE).reshape(-1))
+    ctx.close()
+
+
+def test_full_size_properties(p25):
+    """BASELINE configs[1] scale (1,024 streams): every stream is a circular shift of one of 8 seeds,
+    so decoded payload multisets must be identical across the streams that share a seed."""
+    base = []
+    for s in range(8):
+        st = tx.control_channel(700 + s, 6, lead_idle=30)
+        base.append(tx.baseband_48k(st.dibits, snr_db=20, seed=s)[0][:22000])
+    S_ = 1024
+    bb = np.stack([np.roll(base[s % 8], 360 * 10 * (s // 8 % 4)) for s in range(S_)])
+    ctx = p25.Context(S_, max_chunk_samples=1024, max_baseband=bb.shape[1])
+    ev = p25.MessageReceiver(ctx).feed(bb)
+    assert (np.diff(ev["stream"].astype(np.int64)) >= 0).all()
+    per = {}
+    for s in range(S_):
+        e = ev[ev["stream"] == s]
+        assert (np.diff(e["sample"].astype(np.int64)) > 0).all()
+        key = sorted(bytes(x["payload"][:12]) for x in e[e["kind"] == 7])
+        per.setdefault((s % 8, s // 8 % 4), key)
+        assert key == per[(s % 8, s // 8 % 4)]
+        assert len(key) >= 12
+    ctx.close()
