@@ -1,0 +1,309 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the P25 baseband hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): 1,024 independent synthetic P25 control-channel IQ streams per
+GPU, 2.4 MS/s cf32 (configs[0]'s sample format), 150 ms = 360,000 samples per stream per step,
+decimated by 50 to 48 kHz, C4FM-demodulated, frame-synchronised and TSBK-decoded.  One step is one
+pass of the hot path (p25cu_process: ddc_fm kernel + decode walker) over that batch, 2.95 GB of input,
+far larger than the 126 MB L2, so every step streams from HBM.  The signal is periodic and
+phase-continuous, so consecutive steps are a continuous transmission and every step decodes real
+TSDUs (checked: 8 events per stream per step, CRCs valid).
+
+  value      whole-job IQ Msamples/s with the input already resident in HBM: device time (CUDA events on
+             the library's stream) of K x p25cu_process plus one final event drain (p25cu_poll).
+  e2e        the same metric through the public call sequence with HOST (pinned) input:
+             each step = p25cu_process(host pointer) [H2D copy inside] + p25cu_poll [D2H of events].
+  roofline   dominant kernel p25_ddc_fm_kernel: algorithmic bytes (8 + 4/50 per input sample) divided by
+             its own CUDA-event time inside the timed region, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the oracle (C++ restatement of the reference chain, -march=native) on a bounded sample
+             of the same workload using every host core.  `--impl reference` runs that arm alone.
+
+Multi-GPU: streams shard by rank with no collective on the data path; rank r owns
+streams [r*1024, (r+1)*1024).  torch.distributed (NCCL) is used only for the barrier and the MAX of the
+per-rank device times.  scaling = weak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "spec")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+STREAMS_PER_GPU = 1024
+FS = 2_400_000
+DECIM = 50
+N_PER_STEP = 360_000          # 150 ms = two 360-dibit TSDUs per stream per step
+N_BASE = 16                   # distinct seeded transmissions; streams are circular shifts of them
+METRIC = "Msamples/s IQ demod+decode (real-time P25 channels = baseband samples/s / 48000)"
+ALG_BYTES_PER_SAMPLE = 8.0 + 4.0 / DECIM     # SURVEY.md section 8(d), DESIGN.md section 4
+
+
+def make_base_streams():
+    from tools import p25tx as tx
+    base = []
+    for b in range(N_BASE):
+        st = tx.control_channel(1000 + b, 2, lead_idle=0)
+        assert len(st.dibits) * 10 * DECIM == N_PER_STEP
+        base.append(tx.modulate_iq_periodic(st.dibits, FS, snr_db=20.0, cfo_cycles=3 * (b - N_BASE // 2), seed=b))
+    return np.stack(base)
+
+
+def fill_streams(dst: np.ndarray, base: np.ndarray, first_stream: int):
+    """dst[s] = circular shift of base[(first_stream + s) % N_BASE]; shift depends on the global stream id."""
+    for s in range(dst.shape[0]):
+        g = first_stream + s
+        sh = (g // N_BASE) * 5003 % N_PER_STEP
+        src = base[g % N_BASE]
+        dst[s, : N_PER_STEP - sh] = src[sh:]
+        dst[s, N_PER_STEP - sh:] = src[:sh]
+
+
+class ClockSampler(threading.Thread):
+    """NVML poll of SM clock / throttle reasons during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_arm(steps: int, warmup: int, iq: np.ndarray | None = None):
+    """Oracle CPU implementation on the host cores (rank 0 only).  Returns (Msamples/s, ms/step, info).
+    Each step is the full 1,024-stream batch of the GPU arm (about 8 core-seconds of work)."""
+    from oracle import pyoracle as po
+    try:
+        po.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    cores = os.cpu_count() or 1
+    L = po.lib(native)
+    L.p25o_set_always_correlate(1)       # the reference correlates on every sample [RECALL], see oracle header
+    n_streams = STREAMS_PER_GPU
+    if iq is None:
+        iq = np.empty((n_streams, N_PER_STEP), dtype=np.complex64)
+        fill_streams(iq, make_base_streams(), 0)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        total, counts, _ = po.batch_run(po.FMT_CF32, True, iq, n_streams, N_PER_STEP, cores, native=native)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        assert total >= 3 * n_streams, "oracle decoded too few events"   # fresh receivers: >= 1 whole TSDU each
+    ms = 1e3 * float(np.mean(times))
+    val = n_streams * N_PER_STEP / (ms * 1e-3) / 1e6
+    info = {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "sample": f"all {n_streams} streams x {N_PER_STEP} samples per step ({steps} timed step(s)), {cores} threads, "
+                      f"oracle built {'-march=native' if native else '-march=x86-64-v3'}; the Rust reference cannot be built here"}
+    return val, ms, info
+
+
+def config_dict(n_gpus: int):
+    return {"workload": "configs[1]: 1024 synthetic P25 control-channel IQ streams per GPU, cf32 2.4 MS/s, 360000 samples "
+                        "(150 ms) per stream per step, /50 -> 48 kHz, C4FM demod + frame sync + NID/TSBK decode",
+            "streams_per_gpu": STREAMS_PER_GPU, "samples_per_stream_per_step": N_PER_STEP, "sample_rate": FS,
+            "decimation": DECIM, "input_format": "cf32", "snr_db": 20, "l2_policy": "inputs (2.95 GB/step) larger than L2",
+            "parallelism": f"streams sharded over {n_gpus} GPU(s), no collective"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, ms, info = cpu_arm(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus), "cpu_baseline": info,
+            "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "realtime_channels": val * 1e6 / DECIM / 48000.0, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import p25rx_b200 as p25
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    S, n, K, W = STREAMS_PER_GPU, N_PER_STEP, args.steps, max(args.warmup, 3)
+    base = make_base_streams()
+    host = torch.empty((S, n, 2), dtype=torch.float32, pin_memory=True)
+    fill_streams(host.numpy().view(np.complex64).reshape(S, n), base, rank * S)
+    dev = host.cuda(non_blocking=False)
+    slots = 8 * (W + K) + 32
+    ctx = p25.Context(S, fmt=p25.FMT_CF32_IQ, decimation=DECIM, max_chunk_samples=n, device=local, event_slots=slots)
+    stream = torch.cuda.ExternalStream(ctx.cuda_stream, device=local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- leg 1: device-resident input ("value") + per-kernel timing for the roofline
+    for _ in range(W):
+        ctx.process(dev, n)
+    ctx.sync()
+    ctx.poll(cap=slots * S)
+    sampler = ClockSampler(local)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    t_end = torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launch_count
+    barrier()
+    sampler.start()
+    with torch.cuda.stream(stream):
+        for k in range(K):
+            ev[k][0].record(stream)
+            ctx.demod(dev, n, want_baseband=False)      # ddc_fm kernel
+            ev[k][1].record(stream)
+            ctx.decode()                                 # decode walker
+            ev[k][2].record(stream)
+        events = ctx.poll(cap=slots * S)                 # event compaction + D2H (synchronises)
+        t_end.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    launches = ctx.launch_count - l0
+    dev_ms = ev[0][0].elapsed_time(t_end)
+    ddc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    walk_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    # correctness of the timed work: 2 TSDUs (2 NIDs + 6 TSBKs) per stream per step, all CRCs valid
+    n_tsbk = int(np.count_nonzero(events["kind"] == p25.EV_TSBK))
+    n_err = int(np.count_nonzero(events["kind"] == p25.EV_ERROR))
+    assert n_tsbk >= 6 * S * K - 6 * S and n_err <= S, (n_tsbk, n_err, len(events))
+    import p25_spec as SP
+    for e in events[events["kind"] == p25.EV_TSBK][:: max(1, n_tsbk // 2000)]:
+        pl = bytes(e["payload"][:12])
+        assert SP.crc_ccitt_p25(pl[:10]) == (pl[10] << 8 | pl[11]), "decoded TSBK fails its CRC"
+
+    # ---------------- leg 2: end to end through the public calls with pinned host input
+    host_np = host.numpy()
+    for _ in range(2):
+        ctx.process(host_np, n)
+        ctx.poll(cap=32 * S)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d2h = 0
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for k in range(K):
+            ctx.process(host_np, n)                      # H2D copy of the step's input happens inside
+            got = ctx.poll(cap=32 * S)                   # D2H of the step's events
+            d2h += got.nbytes + 8
+        e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    t = torch.tensor([dev_ms, e2e_ms, ddc_ms, walk_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, ddc_ms, walk_ms = [float(x) for x in t.tolist()]
+    total_samples = world * S * n * K
+    value = total_samples / (dev_ms * 1e-3) / 1e6
+    e2e_value = total_samples / (e2e_ms * 1e-3) / 1e6
+
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes = S * n * ALG_BYTES_PER_SAMPLE
+    achieved = alg_bytes / (ddc_ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(world),
+            "realtime_channels": value * 1e6 / DECIM / 48000.0,
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": S * n * 8, "d2h_bytes_per_step": d2h // K,
+                    "ms_per_step": e2e_ms / K},
+            "gpu_launches": int(launches),
+            "kernels": {"p25_ddc_fm_kernel_ms": ddc_ms, "p25_walk_kernel_ms": walk_ms, "step_ms": dev_ms / K},
+            "roofline": {"kernel": "p25_ddc_fm_kernel<front=/10, cf32>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "clocks": sampler.result(), "events_checked": {"tsbk": n_tsbk, "errors": n_err}}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ddc_fm_traffic.json")) as f:
+            tr = json.load(f)
+            line["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    ctx.close()
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            _, _, info = cpu_arm(1, 0, host.numpy().view(np.complex64).reshape(S, n))
+            line["cpu_baseline"] = info
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

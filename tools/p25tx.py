@@ -290,6 +290,42 @@ def modulate_iq(dibits: np.ndarray, fs: int, snr_db: float | None = 30.0, cfo_hz
     return iq.astype(np.complex64)
 
 
+def modulate_iq_periodic(dibits: np.ndarray, fs: int, snr_db: float | None = 30.0, cfo_cycles: int = 0, seed: int = 0,
+                          amplitude: float = 0.5) -> np.ndarray:
+    """One period of a seamlessly repeating C4FM signal: the symbol shaping is circular and the
+    carrier offset is trimmed so that the phase advances by a whole number of turns per period.
+    Feeding the returned buffer over and over is a continuous transmission of `dibits` repeated
+    (bench.py uses this so that every timed step sees a valid, phase-continuous signal).
+    cfo_cycles: additional whole carrier turns per period (CFO = cfo_cycles / period)."""
+    global _PULSE
+    if _PULSE is None:
+        _PULSE = _c4fm_pulse_48k()
+    assert fs % S.BASEBAND_SAMPLE_RATE == 0
+    L = fs // S.BASEBAND_SAMPLE_RATE
+    n48 = len(dibits) * S.SPS
+    up = np.zeros(n48)
+    up[:: S.SPS] = dibits_to_symbols(dibits) * S.SYMBOL_DEVIATION_HZ
+    pulse = np.zeros(n48)
+    half = len(_PULSE) // 2
+    pulse[: half + 1] = _PULSE[half:]
+    pulse[-half:] = _PULSE[:half]
+    spec = np.fft.rfft(up) * np.fft.rfft(pulse)                  # circular shaping at 48 kHz
+    full = np.zeros(n48 * L // 2 + 1, dtype=np.complex128)
+    full[: len(spec)] = spec
+    if n48 % 2 == 0:
+        full[len(spec) - 1] *= 0.5
+    dev = np.fft.irfft(full, n48 * L) * L                         # band-limited interpolation to fs
+    turns = np.sum(dev) / fs                                      # carrier turns per period from the data
+    trim = (np.round(turns) - turns + cfo_cycles) * fs / len(dev)  # Hz
+    phase = 2.0 * np.pi * np.cumsum(dev + trim) / fs
+    rng = np.random.default_rng(seed)
+    iq = amplitude * np.exp(1j * (phase + rng.uniform(0, 2 * np.pi)))
+    if snr_db is not None:
+        sigma2 = amplitude ** 2 / 10 ** (snr_db / 10) * (fs / 12500.0)
+        iq = iq + np.sqrt(sigma2 / 2) * (rng.standard_normal(len(iq)) + 1j * rng.standard_normal(len(iq)))
+    return iq.astype(np.complex64)
+
+
 def iq_to_u8(iq: np.ndarray) -> np.ndarray:
     """RTL-SDR style interleaved unsigned bytes (src/sdr.rs:25-33, src/demod.rs:72-84)."""
     v = np.empty(2 * len(iq), dtype=np.float32)
