@@ -130,6 +130,9 @@ int p25cu_process(p25cu_ctx* ctx, const void* iq, size_t n_in_per_stream, int iq
  * reference's feed() returns them.  Waits for queued GPU work.  *n receives the number written;
  * returns P25CU_ERR_OVERFLOW (after writing what fits) if cap was too small or slots overflowed. */
 int p25cu_poll(p25cu_ctx* ctx, p25cu_event* out, size_t cap, size_t* n);
+/* Zero-copy variant: *events points at ctx-owned pinned host memory holding all queued events in the same
+ * order; valid until the next p25cu_poll / p25cu_poll_view / p25cu_destroy on this context. */
+int p25cu_poll_view(p25cu_ctx* ctx, const p25cu_event** events, size_t* n);
 /* Number of events p25cu_poll would return now (waits for queued GPU work). */
 int p25cu_pending(p25cu_ctx* ctx, size_t* n);
 
@@ -143,6 +146,10 @@ int p25cu_get_stats(p25cu_ctx* ctx, uint32_t stream, p25cu_stats* out, int clear
  * as void*), a wait for it, and the number of kernel launches issued so far. */
 void* p25cu_cuda_stream(p25cu_ctx* ctx);
 int p25cu_sync(p25cu_ctx* ctx);
+/* Pipelining of consecutive chunks (default on): the decode walker of chunk k runs on a second CUDA stream
+ * concurrently with the demod kernel of chunk k+1 (double-buffered baseband).  Results do not depend on it.
+ * on = 0 serialises both kernels on the stream returned by p25cu_cuda_stream (per-kernel timing). */
+int p25cu_set_overlap(p25cu_ctx* ctx, int on);
 uint64_t p25cu_launch_count(const p25cu_ctx* ctx);
 /* Device pointer/row stride (in floats) of the baseband produced by the last p25cu_demod. */
 int p25cu_device_baseband(p25cu_ctx* ctx, const float** ptr, size_t* row_stride, size_t* n_out);

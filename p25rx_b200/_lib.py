@@ -23,7 +23,7 @@ assert EVENT_DTYPE.itemsize == 80
 
 # names every build must export (checked by tests/test_abi.py against include/p25cu.h)
 EXPORTS = ["p25cu_create", "p25cu_destroy", "p25cu_last_error", "p25cu_demod", "p25cu_decode", "p25cu_process",
-           "p25cu_poll", "p25cu_pending", "p25cu_resync", "p25cu_get_stats", "p25cu_cuda_stream", "p25cu_sync",
+           "p25cu_poll", "p25cu_poll_view", "p25cu_pending", "p25cu_resync", "p25cu_get_stats", "p25cu_cuda_stream", "p25cu_sync", "p25cu_set_overlap",
            "p25cu_launch_count", "p25cu_device_baseband", "p25cu_fec_selftest"]
 
 
@@ -71,12 +71,14 @@ def lib() -> C.CDLL:
     L.p25cu_decode.argtypes = [vp, vp, sz]
     L.p25cu_process.argtypes = [vp, vp, sz, i]
     L.p25cu_poll.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.p25cu_poll_view.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     L.p25cu_pending.argtypes = [vp, C.POINTER(sz)]
     L.p25cu_resync.argtypes = [vp, C.c_uint32]
     L.p25cu_get_stats.argtypes = [vp, C.c_uint32, C.POINTER(Stats), i]
     L.p25cu_cuda_stream.argtypes = [vp]
     L.p25cu_cuda_stream.restype = vp
     L.p25cu_sync.argtypes = [vp]
+    L.p25cu_set_overlap.argtypes = [vp, i]
     L.p25cu_launch_count.argtypes = [vp]
     L.p25cu_launch_count.restype = C.c_uint64
     L.p25cu_device_baseband.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]

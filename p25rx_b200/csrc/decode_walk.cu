@@ -25,10 +25,24 @@
 
 __constant__ float c_sync_fp[P25_FP_LEN];
 
+#define SEARCH_N 128                          // candidate positions per search step (4 per lane)
+#define WIN_LEN (P25_FP_LEN - 1 + SEARCH_N)  // samples needed to correlate them
+
 struct WalkShared {
     P25DevTables T;
     WalkState ws[P25CU_WALK_WARPS];
+    float win[P25CU_WALK_WARPS][WIN_LEN + 2];
 };
+
+// packed pair of IEEE fused multiply-adds (one FFMA2): each half is exactly fmaf()
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&r);
+}
 static_assert(sizeof(P25DevTables) % 16 == 0, "tables are staged with 16-byte copies");
 
 struct WarpCtx {
@@ -85,14 +99,9 @@ __device__ __forceinline__ void fail(const WarpCtx& c, unsigned code, unsigned l
     enter_sync(*c.ws, idx + 1);
 }
 
-// NID complete (32 dibits in ws.buf).  PacketNID event, reference src/recv.rs:216-222.
-__device__ __noinline__ void complete_nid(const WarpCtx& c, unsigned long long idx) {
+// NID complete (32 dibits in ws.buf).  PacketNID event, reference src/recv.rs:216-222.  Called by the whole warp.
+__device__ __forceinline__ void nid_apply(const WarpCtx& c, unsigned long long idx, int nerr, unsigned data) {  // lane 0
     WalkState& ws = *c.ws;
-    const P25DevTables& T = *c.T;
-    unsigned long long bits = 0;
-    for (int i = 0; i < P25_NID_DIBITS; i++) bits = (bits << 2) | ws.buf[i];
-    unsigned data;
-    const int nerr = p25_bch_decode(T, bits >> 1, &data);
     if (nerr < 0) {
         stat_bad(c, P25CU_ST_BCH);
         fail(c, P25CU_E_BCH, idx);
@@ -119,26 +128,162 @@ __device__ __noinline__ void complete_nid(const WarpCtx& c, unsigned long long i
     emit(c, P25CU_EV_NID, idx, pl, 3);
 }
 
+// ---------------------------------------------------------------- warp-cooperative decoders
+// BCH(63,16,23), all 32 lanes: lanes 0..21 each sum one syndrome, lane 0 runs Berlekamp-Massey only when a
+// syndrome is non-zero, the Chien search covers two positions per lane.  Same bounded-distance result as
+// p25_bch_decode (the per-thread form used by the unit kernels).  Returns corrected bits or -1, uniformly.
+__device__ __forceinline__ unsigned warp_bch_syndromes(const P25DevTables& T, unsigned long long w, int lane) {
+    const int j = lane + 1;
+    int acc = 0, e = 0;
+    if (lane < 2 * P25_BCH_T) {
+        for (int i = 0; i < 63; i++) {
+            if ((w >> i) & 1) acc ^= T.gf_exp[e];
+            e += j;
+            if (e >= 63) e -= 63;
+            if (e >= 63) e -= 63;
+        }
+    }
+    return (unsigned)acc;
+}
+
+__device__ __noinline__ int warp_bch_decode(const P25DevTables& T, unsigned char* scratch, unsigned long long word63, int lane,
+                                            unsigned* data16) {
+    unsigned long long w = word63 & 0x7FFFFFFFFFFFFFFFULL;
+    const unsigned syn = warp_bch_syndromes(T, w, lane);
+    int fixed = 0;
+    if (__ballot_sync(FULL, syn != 0)) {
+        if (lane < 2 * P25_BCH_T) scratch[lane] = (unsigned char)syn;
+        __syncwarp();
+        int L = 0;
+        if (lane == 0) {
+            unsigned char S[2 * P25_BCH_T], lam[2 * P25_BCH_T + 1];
+            for (int i = 0; i < 2 * P25_BCH_T; i++) S[i] = scratch[i];
+            L = p25_berlekamp_massey<2 * P25_BCH_T>(T, S, lam);
+            for (int i = 0; i <= P25_BCH_T; i++) scratch[32 + i] = lam[i];
+        }
+        L = __shfl_sync(FULL, L, 0);
+        __syncwarp();
+        if (L > P25_BCH_T) return -1;
+        unsigned char lam[P25_BCH_T + 1];
+        for (int i = 0; i <= P25_BCH_T; i++) lam[i] = scratch[32 + i];
+        const int p1 = lane, p2 = lane + 32;
+        const bool r1 = p25_poly_eval(T, lam, L, T.gf_exp[(63 - p1) % 63]) == 0;
+        const bool r2 = p2 < 63 && p25_poly_eval(T, lam, L, T.gf_exp[(63 - p2) % 63]) == 0;
+        const unsigned lo = __ballot_sync(FULL, r1), hi = __ballot_sync(FULL, r2);
+        if (__popc(lo) + __popc(hi) != L) return -1;
+        w ^= (unsigned long long)lo | ((unsigned long long)hi << 32);
+        if (__ballot_sync(FULL, warp_bch_syndromes(T, w, lane) != 0)) return -1;
+        fixed = L;
+    }
+    *data16 = (unsigned)(w >> 47);
+    return fixed;
+}
+
+// Half-rate trellis, 16 lanes = (next state, previous state) pairs; add-compare-select by two shuffle
+// steps on the key (path metric << 2 | previous state), which keeps the lowest predecessor on ties exactly
+// like p25_trellis_half_decode.  Survivors: one byte per step in scratch, traced back by lane 0.
+__device__ __noinline__ int warp_trellis_half_decode(const P25DevTables& T, unsigned char* scratch, const unsigned char* dibits,
+                                                     int lane, unsigned char* out12) {
+    // deinterleave: lane holds received symbols lane and lane + 32
+    int s0 = 0, s1 = 0;
+    {
+        const int slot = T.interleave[lane];
+        s0 = (dibits[2 * slot] << 2) | dibits[2 * slot + 1];
+        if (lane + 32 < 49) {
+            const int slot1 = T.interleave[lane + 32];
+            s1 = (dibits[2 * slot1] << 2) | dibits[2 * slot1 + 1];
+        }
+    }
+    // Exact shortcut: the 16 (previous state, next state) transitions emit 16 distinct symbols, so every
+    // received symbol names one transition.  If consecutive transitions chain up from state 0 to state 0 the
+    // received block is a code word (metric 0) and, the free distance being 5, Viterbi would return exactly
+    // this path.  Fully parallel; the add-compare-select loop below only runs for blocks with bit errors.
+    {
+        int t0i = 0, t1i = 0;   // transition index prev*4+next of symbols lane and lane+32
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            const int pr = T.trellis_pair[t];
+            if (pr == s0) t0i = t;
+            if (pr == s1) t1i = t;
+        }
+        const int nx0 = t0i & 3, nx1 = t1i & 3;
+        int pv0 = __shfl_up_sync(FULL, nx0, 1), pv1 = __shfl_up_sync(FULL, nx1, 1);
+        const int last0 = __shfl_sync(FULL, nx0, 31);
+        if (lane == 0) {
+            pv0 = 0;
+            pv1 = last0;
+        }
+        bool ok = (t0i >> 2) == pv0;
+        if (lane + 32 < 49) ok = ok && (t1i >> 2) == pv1;
+        if (lane == 16) ok = ok && nx1 == 0;   // step 48 = the flush dibit
+        if (__all_sync(FULL, ok)) {
+            // dibit i = next state of step i; pack 4 dibits per byte
+            unsigned v0 = (unsigned)nx0 << (6 - 2 * (lane & 3)), v1 = (lane + 32 < 48) ? (unsigned)nx1 << (6 - 2 * (lane & 3)) : 0u;
+            v0 |= __shfl_xor_sync(FULL, v0, 1);
+            v0 |= __shfl_xor_sync(FULL, v0, 2);
+            v1 |= __shfl_xor_sync(FULL, v1, 1);
+            v1 |= __shfl_xor_sync(FULL, v1, 2);
+            if ((lane & 3) == 0) {
+                out12[lane >> 2] = (unsigned char)v0;
+                if (lane < 16) out12[8 + (lane >> 2)] = (unsigned char)v1;
+            }
+            __syncwarp();
+            return 0;
+        }
+    }
+    const int ns = (lane >> 2) & 3, ps = lane & 3;
+    const int expect = T.trellis_pair[ps * 4 + ns];
+    int m = ps == 0 ? 0 : (1 << 20);   // metric of state `ps` as seen by this lane
+    for (int i = 0; i < 49; i++) {
+        const int sym = __shfl_sync(FULL, i < 32 ? s0 : s1, i & 31);
+        int key = ((m + __popc(expect ^ sym)) << 2) | ps;
+        key = min(key, __shfl_xor_sync(FULL, key, 1));
+        key = min(key, __shfl_xor_sync(FULL, key, 2));
+        // key now holds the winner for next state `ns` in all four lanes of the group
+        const unsigned b0 = __ballot_sync(FULL, key & 1), b1 = __ballot_sync(FULL, key & 2);
+        if (lane == 0) {
+            unsigned f = 0;
+#pragma unroll
+            for (int g = 0; g < 4; g++) f |= ((((b0 >> (4 * g)) & 1u) | (((b1 >> (4 * g)) & 1u) << 1)) << (2 * g));
+            scratch[i] = (unsigned char)f;
+        }
+        m = __shfl_sync(FULL, key >> 2, ps * 4);   // new metric of state ps lives in group ps
+    }
+    const int m0 = __shfl_sync(FULL, m, 0);        // lane 0 has ps = 0
+    __syncwarp();
+    if (m0 > P25_VITERBI_MAX_FIX) return -1;
+    if (lane == 0) {
+        for (int i = 0; i < 12; i++) out12[i] = 0;
+        int st = 0;
+        for (int i = 48; i >= 0; i--) {
+            if (i < 48) out12[i >> 2] |= (unsigned char)(st << (6 - 2 * (i & 3)));
+            st = (scratch[i] >> (2 * st)) & 3;
+        }
+    }
+    __syncwarp();
+    return m0;
+}
+
+// TSBK block decoded by the warp (reference src/recv.rs:231); lane 0 applies the result.
+__device__ __forceinline__ void tsbk_apply(const WarpCtx& c, unsigned long long idx, int fixed, const unsigned char* out) {
+    WalkState& ws = *c.ws;
+    ws.cnt = 0;
+    if (fixed < 0) {
+        stat_bad(c, P25CU_ST_VITERBI_DIBIT);
+        fail(c, P25CU_E_VITERBI_DIBIT, idx);
+        return;
+    }
+    stat_ok(c, P25CU_ST_VITERBI_DIBIT, (unsigned)fixed);
+    ws.blocks++;
+    if ((out[0] & 0x80) || ws.blocks == 3) ws.state = WS_FLUSH;
+    emit(c, P25CU_EV_TSBK, idx, out, 12);
+}
+
 // A payload decision point has been reached (ws.cnt == target).
 __device__ __noinline__ void complete_payload(const WarpCtx& c, unsigned long long idx) {
     WalkState& ws = *c.ws;
     const P25DevTables& T = *c.T;
     switch (ws.duid) {
-        case 0x7: {  // TSBK -> TrunkingControl (reference src/recv.rs:231)
-            unsigned char out[12];
-            const int fixed = p25_trellis_half_decode(T, ws.buf, out);
-            ws.cnt = 0;
-            if (fixed < 0) {
-                stat_bad(c, P25CU_ST_VITERBI_DIBIT);
-                fail(c, P25CU_E_VITERBI_DIBIT, idx);
-                return;
-            }
-            stat_ok(c, P25CU_ST_VITERBI_DIBIT, (unsigned)fixed);
-            ws.blocks++;
-            if ((out[0] & 0x80) || ws.blocks == 3) ws.state = WS_FLUSH;
-            emit(c, P25CU_EV_TSBK, idx, out, 12);
-            return;
-        }
         case 0x0: {  // HDU -> VoiceHeader (reference src/recv.rs:223)
             for (int w = 0; w < 36; w++) {
                 unsigned d6;
@@ -234,7 +379,7 @@ __device__ __noinline__ void complete_payload(const WarpCtx& c, unsigned long lo
 }
 
 // ---------------------------------------------------------------- the walker
-__global__ void __launch_bounds__(32 * P25CU_WALK_WARPS) p25_walk_kernel(const WalkParams p) {
+__global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(const WalkParams p) {
     __shared__ WalkShared sh;
     {
         const uint4* src = (const uint4*)p.tables;
@@ -254,6 +399,7 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS) p25_walk_kernel(const W
     if (!active) return;
 
     WarpCtx c{&p, &sh.T, &ws, stream};
+    float* win = sh.win[warp];
     const unsigned long long p0 = p.p0, end = p.p0 + p.n;
     const float* row = p.bb + (size_t)stream * p.row_stride;  // row[i] <-> absolute sample p0 - 256 + i
     const unsigned lane_le = 0xFFFFFFFFu >> (31 - lane);
@@ -270,37 +416,58 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS) p25_walk_kernel(const W
     for (;;) {
         const int st = ws.state;
         if (st == WS_SYNC) {
-            // ---- frame-sync search over 32 positions
+            // ---- frame-sync search over 128 positions: lane l owns positions pos + l + 32*h, h = 0..3
             const unsigned long long pos = ws.pos;
             if (pos >= end) break;
-            const unsigned long long n_abs = pos + lane;
-            const bool valid = n_abs < end;
-            float corr = 0.f, en = 0.f;
-            if (valid) {
-                const float* w = row + (long long)(n_abs - p0) + P25CU_BB_HIST - (P25_FP_LEN - 1);
-#pragma unroll
+            const long long wbase = (long long)(pos - p0) + P25CU_BB_HIST - (P25_FP_LEN - 1);   // row index of win[0]
+            const long long wlim = (long long)P25CU_BB_HIST + (long long)p.n;                   // first invalid row index
+            __syncwarp();
+            for (int i = lane; i < WIN_LEN; i += 32) win[i] = (wbase + i < wlim) ? __ldg(row + wbase + i) : 0.f;
+            __syncwarp();
+            float2 cA = make_float2(0.f, 0.f), cB = cA, eA = cA, eB = cA;   // A: h = 0,1   B: h = 2,3
+            {
+                const float* w1 = win + lane;
+#pragma unroll 11
                 for (int k = 0; k < P25_FP_LEN; k++) {
-                    const float x = __ldg(w + k);
-                    corr = fmaf(c_sync_fp[k], x, corr);
-                    en = fmaf(x, x, en);
+                    const float2 xa = make_float2(w1[k], w1[k + 32]), xb = make_float2(w1[k + 64], w1[k + 96]);
+                    const float2 f = make_float2(c_sync_fp[k], c_sync_fp[k]);
+                    cA = fma2(f, xa, cA);
+                    cB = fma2(f, xb, cB);
+                    eA = fma2(xa, xa, eA);
+                    eB = fma2(xb, xb, eB);
                 }
             }
-            const bool above = valid && corr > 0.f && (corr * corr >= P25_SYNC_RHO2_EFP * en);
-            float pc = __shfl_up_sync(FULL, corr, 1);
-            int pa = __shfl_up_sync(FULL, (int)above, 1);
-            int hp = 1;
-            if (lane == 0) {
-                pc = ws.prev_corr;
-                pa = ws.prev_above;
-                hp = ws.have_prev;
+            const unsigned long long left = end - pos;
+            const int nvalid = left < SEARCH_N ? (int)left : SEARCH_N;
+            const float corr[4] = {cA.x, cA.y, cB.x, cB.y}, en[4] = {eA.x, eA.y, eB.x, eB.y};
+            int fire_off = -1;
+            float pcn = ws.prev_corr;      // predecessor of lane 0 in the current quarter
+            int pan = ws.prev_above, hpn = ws.have_prev;
+            float lc = 0.f;
+            int la = 0;
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+                const bool v = lane + 32 * h < nvalid;
+                const bool ab = v && corr[h] > 0.f && (corr[h] * corr[h] >= P25_SYNC_RHO2_EFP * en[h]);
+                float pc = __shfl_up_sync(FULL, corr[h], 1);
+                int pa = __shfl_up_sync(FULL, (int)ab, 1), hp = 1;
+                if (lane == 0) {
+                    pc = pcn;
+                    pa = pan;
+                    hp = hpn;
+                }
+                const unsigned fm = __ballot_sync(FULL, v && hp && ab && pa && corr[h] <= pc);
+                if (fm && fire_off < 0) fire_off = 32 * h + __ffs(fm) - 1;
+                // hand the last position of this quarter to lane 0 of the next one
+                pcn = __shfl_sync(FULL, corr[h], 31);
+                pan = __shfl_sync(FULL, (int)ab, 31);
+                hpn = 1;
+                if (nvalid - 1 >= 32 * h && nvalid - 1 < 32 * h + 32) {
+                    lc = __shfl_sync(FULL, corr[h], (nvalid - 1) & 31);
+                    la = __shfl_sync(FULL, (int)ab, (nvalid - 1) & 31);
+                }
             }
-            const bool fire = valid && hp && above && pa && corr <= pc;
-            const unsigned fm = __ballot_sync(FULL, fire);
-            if (fm == 0) {
-                const unsigned long long left = end - pos;
-                const int nvalid = left < 32 ? (int)left : 32;
-                const float lc = __shfl_sync(FULL, corr, nvalid - 1);
-                const int la = __shfl_sync(FULL, (int)above, nvalid - 1);
+            if (fire_off < 0) {
                 __syncwarp();
                 if (lane == 0) {
                     ws.prev_corr = lc;
@@ -312,7 +479,7 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS) p25_walk_kernel(const W
                 continue;
             }
             // ---- lock: the correlation peaked on the sample before the firing one
-            const unsigned long long idx = pos + (__ffs(fm) - 1);
+            const unsigned long long idx = pos + fire_off;
             const long long pk = (long long)idx - 1;
             float v = 0.f;
             if (lane < P25_FS_DIBITS) v = row[(pk - (long long)p0) + P25CU_BB_HIST - (P25_FP_LEN - 1) + P25_SPS * lane];
@@ -361,49 +528,78 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS) p25_walk_kernel(const W
             target = 0x7FFFFFFF;
         }
         const int need = target - cnt;
+        // 64 symbol instants per step: lane l slices instants l and 32 + l
         const unsigned long long span = (end - 1 - t0) / P25_SPS + 1;
-        const int avail = span < 32 ? (int)span : 32;
-        const bool valid = lane < avail;
-        const bool status = ((fpos0 + lane) % P25_STATUS_PERIOD) == P25_STATUS_PERIOD - 1;
-        float s = 0.f;
-        if (valid) s = __ldg(row + (long long)(t0 - p0) + P25CU_BB_HIST + P25_SPS * lane);
-        const int d = s > ws.pth ? 1 : (s > ws.mid ? 0 : (s > ws.nth ? 2 : 3));  // [STD] 01 +3, 00 +1, 10 -1, 11 -3
-        const unsigned dmask = __ballot_sync(FULL, valid && !status);
-        const int c_incl = __popc(dmask & lane_le);
-        const unsigned stopmask = (st == WS_FLUSH) ? __ballot_sync(FULL, valid && status)
-                                                   : __ballot_sync(FULL, valid && !status && c_incl == need);
-        const int K = stopmask ? __ffs(stopmask) : avail;
-        if (st != WS_FLUSH && lane < K && valid && !status) ws.buf[cnt + c_incl - 1] = (unsigned char)d;
-        const int ndata = __popc(dmask & (K >= 32 ? FULL : ((1u << K) - 1u)));
+        const int avail = span < 64 ? (int)span : 64;
+        const bool va = lane < avail, vb = lane + 32 < avail;
+        const bool sta = ((fpos0 + lane) % P25_STATUS_PERIOD) == P25_STATUS_PERIOD - 1;
+        const bool stb = ((fpos0 + 32 + lane) % P25_STATUS_PERIOD) == P25_STATUS_PERIOD - 1;
+        const float* sp = row + (long long)(t0 - p0) + P25CU_BB_HIST + P25_SPS * lane;
+        const float sa = va ? __ldg(sp) : 0.f, sb = vb ? __ldg(sp + 32 * P25_SPS) : 0.f;
+        const float pth = ws.pth, mid = ws.mid, nth = ws.nth;
+        const int da = sa > pth ? 1 : (sa > mid ? 0 : (sa > nth ? 2 : 3));   // [STD] 01 +3, 00 +1, 10 -1, 11 -3
+        const int db = sb > pth ? 1 : (sb > mid ? 0 : (sb > nth ? 2 : 3));
+        const unsigned dm_a = __ballot_sync(FULL, va && !sta), dm_b = __ballot_sync(FULL, vb && !stb);
+        const int ca = __popc(dm_a & lane_le), cb = __popc(dm_a) + __popc(dm_b & lane_le);
+        unsigned st_a, st_b;
+        if (st == WS_FLUSH) {
+            st_a = __ballot_sync(FULL, va && sta);
+            st_b = __ballot_sync(FULL, vb && stb);
+        } else {
+            st_a = __ballot_sync(FULL, va && !sta && ca == need);
+            st_b = __ballot_sync(FULL, vb && !stb && cb == need);
+        }
+        const unsigned stopmask = st_a | st_b;
+        const int K = st_a ? __ffs(st_a) : (st_b ? 32 + __ffs(st_b) : avail);
+        if (st != WS_FLUSH) {
+            if (lane < K && va && !sta) ws.buf[cnt + ca - 1] = (unsigned char)da;
+            if (lane + 32 < K && vb && !stb) ws.buf[cnt + cb - 1] = (unsigned char)db;
+        }
+        const unsigned mk_a = K >= 32 ? FULL : ((1u << K) - 1u);
+        const unsigned mk_b = K <= 32 ? 0u : (K >= 64 ? FULL : ((1u << (K - 32)) - 1u));
+        const int ndata = __popc(dm_a & mk_a) + __popc(dm_b & mk_b);
         __syncwarp();
         if (lane == 0) {
             ws.next_sym = t0 + (unsigned long long)P25_SPS * K;
             ws.frame_pos = fpos0 + K;
             if (st != WS_FLUSH) ws.cnt = cnt + ndata;
-            if (stopmask) {
-                const unsigned long long idx = t0 + (unsigned long long)P25_SPS * (K - 1);
-                if (st == WS_FLUSH) enter_sync(ws, idx + 1);
-                else if (st == WS_NID) complete_nid(c, idx);
-                else complete_payload(c, idx);
-            }
         }
         __syncwarp();
+        if (stopmask) {
+            const unsigned long long idx = t0 + (unsigned long long)P25_SPS * (K - 1);
+            if (st == WS_FLUSH) {
+                if (lane == 0) enter_sync(ws, idx + 1);
+            } else if (st == WS_NID) {
+                unsigned long long bits = 0;
+                for (int i = 0; i < P25_NID_DIBITS; i++) bits = (bits << 2) | ws.buf[i];
+                unsigned data = 0;
+                const int nerr = warp_bch_decode(sh.T, ws.scratch, bits >> 1, lane, &data);
+                if (lane == 0) nid_apply(c, idx, nerr, data);
+            } else if (ws.duid == 0x7) {
+                unsigned char* out = ws.hex;   // 12-byte result area
+                const int fixed = warp_trellis_half_decode(sh.T, ws.scratch, ws.buf, lane, out);
+                if (lane == 0) tsbk_apply(c, idx, fixed, out);
+            } else {
+                if (lane == 0) complete_payload(c, idx);
+            }
+            __syncwarp();
+        }
     }
 
-    // ---- end of chunk: persist state, roll the last 256 samples to the front of the row
+    // ---- end of chunk: persist state, hand the last 256 samples to the front of the next chunk's row
     __syncwarp();
     {
         uint4* dst = (uint4*)(p.states + stream);
         const uint4* src = (const uint4*)&ws;
         for (unsigned i = lane; i < sizeof(WalkState) / 16; i += 32) dst[i] = src[i];
     }
-    float* rw = p.bb_rw + (size_t)stream * p.row_stride;
+    float* nxt = p.bb_next + (size_t)stream * p.row_stride;
     float keep[P25CU_BB_HIST / 32];
 #pragma unroll
-    for (int i = 0; i < P25CU_BB_HIST / 32; i++) keep[i] = rw[p.n + lane + 32 * i];
+    for (int i = 0; i < P25CU_BB_HIST / 32; i++) keep[i] = row[p.n + lane + 32 * i];
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < P25CU_BB_HIST / 32; i++) rw[lane + 32 * i] = keep[i];
+    for (int i = 0; i < P25CU_BB_HIST / 32; i++) nxt[lane + 32 * i] = keep[i];
 }
 
 cudaError_t p25cu_walk_upload_consts() {

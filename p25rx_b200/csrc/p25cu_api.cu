@@ -17,7 +17,10 @@ cudaError_t p25cu_walk_upload_consts();
 
 struct p25cu_ctx {
     p25cu_config cfg;
-    cudaStream_t stream;
+    cudaStream_t stream;       // input copies + ddc_fm kernel
+    cudaStream_t stream2;      // decode walker, event compaction, event/stat copies
+    cudaEvent_t ev_bb_ready[2], ev_bb_free[2];
+    int overlap;               // walker of chunk k runs concurrently with ddc_fm of chunk k+1
     char err[512];
     unsigned ht;               // input tail length (samples)
     size_t max_out;            // max baseband samples per stream per chunk
@@ -27,7 +30,9 @@ struct p25cu_ctx {
     size_t d_iq_bytes;
     float2* d_tail[2];
     int tail_cur;
-    float* d_bb;
+    float* d_bb[2];            // double-buffered baseband rows
+    int bb_cur;                // buffer the next producer (demod / host baseband) writes
+    int bb_last;               // buffer holding the newest undecoded baseband
     float* d_power;
     WalkState* d_states;
     p25cu_event* d_slots;
@@ -35,6 +40,8 @@ struct p25cu_ctx {
     unsigned* d_offsets;       // [S + 2]: exclusive offsets, total, overflow flag
     unsigned* d_stats;
     P25DevTables* d_tables;
+    p25cu_event* h_events;     // pinned staging for polls (grown on demand)
+    size_t h_events_cap;
     unsigned long long a_abs;  // input samples consumed per stream
     unsigned long long p_abs;  // baseband samples decoded per stream
     size_t last_n_out;
@@ -65,10 +72,12 @@ extern "C" void p25cu_destroy(p25cu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     cudaFree(ctx->d_iq);
     cudaFree(ctx->d_tail[0]);
     cudaFree(ctx->d_tail[1]);
-    cudaFree(ctx->d_bb);
+    cudaFree(ctx->d_bb[0]);
+    cudaFree(ctx->d_bb[1]);
     cudaFree(ctx->d_power);
     cudaFree(ctx->d_states);
     cudaFree(ctx->d_slots);
@@ -76,7 +85,13 @@ extern "C" void p25cu_destroy(p25cu_ctx* ctx) {
     cudaFree(ctx->d_offsets);
     cudaFree(ctx->d_stats);
     cudaFree(ctx->d_tables);
+    cudaFreeHost(ctx->h_events);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_bb_ready[i]) cudaEventDestroy(ctx->ev_bb_ready[i]);
+        if (ctx->ev_bb_free[i]) cudaEventDestroy(ctx->ev_bb_free[i]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
 
@@ -94,7 +109,17 @@ static int create_impl(p25cu_ctx* ctx) {
         return P25CU_ERR_CUDA;
     }
     ctx->n_sm = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {   // the HBM-bound demod kernel gets the SMs first; the latency-bound walker fills what is left
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, lo));
+    }
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_bb_ready[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_bb_free[i], cudaEventDisableTiming));
+    }
+    ctx->overlap = 1;
     const size_t S = cfg.n_streams;
     ctx->ht = p25cu_ddc_tail_len(cfg.decimation);
     ctx->max_out = cfg.max_chunk_samples / cfg.decimation + 1;
@@ -106,8 +131,10 @@ static int create_impl(p25cu_ctx* ctx) {
     CK(cudaMalloc(&ctx->d_tail[1], S * ctx->ht * sizeof(float2)));
     CK(cudaMemsetAsync(ctx->d_tail[0], 0, S * ctx->ht * sizeof(float2), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_tail[1], 0, S * ctx->ht * sizeof(float2), ctx->stream));
-    CK(cudaMalloc(&ctx->d_bb, S * ctx->row_stride * sizeof(float)));
-    CK(cudaMemsetAsync(ctx->d_bb, 0, S * ctx->row_stride * sizeof(float), ctx->stream));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaMalloc(&ctx->d_bb[i], S * ctx->row_stride * sizeof(float)));
+        CK(cudaMemsetAsync(ctx->d_bb[i], 0, S * ctx->row_stride * sizeof(float), ctx->stream));
+    }
     CK(cudaMalloc(&ctx->d_power, S * sizeof(float)));
     CK(cudaMalloc(&ctx->d_states, S * sizeof(WalkState)));
     CK(cudaMemsetAsync(ctx->d_states, 0, S * sizeof(WalkState), ctx->stream));  // state SYNC, pos 0
@@ -128,6 +155,13 @@ static int create_impl(p25cu_ctx* ctx) {
     }
     CK(p25cu_ddc_upload_taps());
     CK(p25cu_walk_upload_consts());
+    {   // pinned staging for polls, sized for a full set of slots (bounded; grown on demand)
+        size_t cap = S * ctx->ev_cap;
+        const size_t lim = ((size_t)512 << 20) / sizeof(p25cu_event);
+        if (cap > lim) cap = lim;
+        CK(cudaHostAlloc((void**)&ctx->h_events, cap * sizeof(p25cu_event), cudaHostAllocDefault));
+        ctx->h_events_cap = cap;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return P25CU_OK;
 }
@@ -190,7 +224,9 @@ extern "C" int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_d
     p.iq = d_in;
     p.tail_in = ctx->d_tail[ctx->tail_cur];
     p.tail_out = ctx->d_tail[ctx->tail_cur ^ 1];
-    p.bb = ctx->d_bb;
+    const int buf = ctx->bb_cur;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_bb_free[buf], 0));   // the walker that last read this buffer is done
+    p.bb = ctx->d_bb[buf];
     p.row_stride = ctx->row_stride;
     p.power_sum = power_dbm ? ctx->d_power : nullptr;
     p.a0 = ctx->a_abs;
@@ -218,12 +254,15 @@ extern "C" int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_d
         ctx->launches++;
         ctx->tail_cur ^= 1;
     }
+    CK(cudaEventRecord(ctx->ev_bb_ready[buf], ctx->stream));
+    ctx->bb_last = buf;
+    ctx->bb_cur = buf ^ 1;
     ctx->a_abs += n;
     ctx->last_n_out = p.n_out;
     ctx->dev_bb_fresh = true;
     if (n_out_p) *n_out_p = p.n_out;
     if (baseband_out && p.n_out)
-        CK(cudaMemcpy2DAsync(baseband_out, p.n_out * sizeof(float), ctx->d_bb + P25CU_BB_HIST, ctx->row_stride * sizeof(float),
+        CK(cudaMemcpy2DAsync(baseband_out, p.n_out * sizeof(float), ctx->d_bb[buf] + P25CU_BB_HIST, ctx->row_stride * sizeof(float),
                              p.n_out * sizeof(float), S, cudaMemcpyDeviceToHost, ctx->stream));
     if (power_dbm) {
         CK(cudaMemcpyAsync(power_dbm, ctx->d_power, S * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -243,23 +282,31 @@ extern "C" int p25cu_decode(p25cu_ctx* ctx, const float* baseband, size_t n) {
     if (!ctx) return P25CU_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     const size_t S = ctx->cfg.n_streams;
+    int buf;
     if (baseband) {
         if (n > ctx->max_out) return fail_arg(ctx, "n_per_stream exceeds the configured maximum");
+        buf = ctx->bb_cur;
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_bb_free[buf], 0));
         if (n)
-            CK(cudaMemcpy2DAsync(ctx->d_bb + P25CU_BB_HIST, ctx->row_stride * sizeof(float), baseband, n * sizeof(float),
+            CK(cudaMemcpy2DAsync(ctx->d_bb[buf] + P25CU_BB_HIST, ctx->row_stride * sizeof(float), baseband, n * sizeof(float),
                                  n * sizeof(float), S, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_bb_ready[buf], ctx->stream));
+        ctx->bb_cur = buf ^ 1;
     } else {
         if (!ctx->dev_bb_fresh) {
             snprintf(ctx->err, sizeof ctx->err, "p25cu_decode(NULL): no undecoded device-resident baseband (call p25cu_demod first)");
             return P25CU_ERR_STATE;
         }
+        buf = ctx->bb_last;
         n = ctx->last_n_out;
     }
     ctx->dev_bb_fresh = false;
+    cudaStream_t ws = ctx->overlap ? ctx->stream2 : ctx->stream;
+    CK(cudaStreamWaitEvent(ws, ctx->ev_bb_ready[buf], 0));
     WalkParams w;
     memset(&w, 0, sizeof w);
-    w.bb = ctx->d_bb;
-    w.bb_rw = ctx->d_bb;
+    w.bb = ctx->d_bb[buf];
+    w.bb_next = ctx->d_bb[buf ^ 1];
     w.row_stride = ctx->row_stride;
     w.p0 = ctx->p_abs;
     w.n = (unsigned)n;
@@ -269,7 +316,9 @@ extern "C" int p25cu_decode(p25cu_ctx* ctx, const float* baseband, size_t n) {
     w.ev_cap = ctx->ev_cap;
     w.stats = ctx->d_stats;
     w.tables = ctx->d_tables;
-    CK(p25cu_launch_walk(w, ctx->stream));
+    CK(p25cu_launch_walk(w, ws));
+    CK(cudaEventRecord(ctx->ev_bb_free[buf], ws));
+    if (!ctx->overlap) CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_bb_free[buf], 0));   // keep stream2 consumers ordered
     ctx->launches++;
     ctx->p_abs += n;
     return P25CU_OK;
@@ -284,11 +333,11 @@ extern "C" int p25cu_process(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on
 static int compact(p25cu_ctx* ctx, bool gather, unsigned* total, unsigned* overflow) {
     const unsigned S = ctx->cfg.n_streams;
     CK(p25cu_launch_compact(ctx->d_states, ctx->d_slots, ctx->ev_cap, S, ctx->d_offsets, gather ? ctx->d_dense : nullptr,
-                            ctx->stream));
+                            ctx->stream2));
     ctx->launches += gather ? 2 : 1;
     unsigned tail[2];
-    CK(cudaMemcpyAsync(tail, ctx->d_offsets + S, sizeof tail, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(tail, ctx->d_offsets + S, sizeof tail, cudaMemcpyDeviceToHost, ctx->stream2));
+    CK(cudaStreamSynchronize(ctx->stream2));
     *total = tail[0];
     *overflow = tail[1];
     return P25CU_OK;
@@ -304,23 +353,55 @@ extern "C" int p25cu_pending(p25cu_ctx* ctx, size_t* n) {
     return P25CU_OK;
 }
 
-extern "C" int p25cu_poll(p25cu_ctx* ctx, p25cu_event* out, size_t cap, size_t* n) {
-    if (!ctx || !n || (!out && cap)) return P25CU_ERR_ARG;
-    CK(cudaSetDevice(ctx->cfg.device));
+// compaction + D2H of all queued events into the pinned staging buffer
+static int drain(p25cu_ctx* ctx, unsigned* total_p) {
     unsigned total, ovf;
     const int rc = compact(ctx, true, &total, &ovf);
     if (rc != P25CU_OK) return rc;
-    const size_t take = total < cap ? total : cap;
-    if (take) {
-        CK(cudaMemcpyAsync(out, ctx->d_dense, take * sizeof(p25cu_event), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+    if (total > ctx->h_events_cap) {
+        cudaFreeHost(ctx->h_events);
+        ctx->h_events = nullptr;
+        ctx->h_events_cap = 0;
+        const size_t cap = (size_t)total + total / 2 + 1024;
+        CK(cudaHostAlloc((void**)&ctx->h_events, cap * sizeof(p25cu_event), cudaHostAllocDefault));
+        ctx->h_events_cap = cap;
     }
-    *n = take;
-    if (ovf || take < total) {
-        snprintf(ctx->err, sizeof ctx->err, "event overflow: %u queued, %zu returned, slot overflow %u", total, take, ovf);
+    if (total) {
+        CK(cudaMemcpyAsync(ctx->h_events, ctx->d_dense, (size_t)total * sizeof(p25cu_event), cudaMemcpyDeviceToHost, ctx->stream2));
+        CK(cudaStreamSynchronize(ctx->stream2));
+    }
+    *total_p = total;
+    if (ovf) {
+        snprintf(ctx->err, sizeof ctx->err, "event slot overflow: events were dropped (raise event_slots)");
         return P25CU_ERR_OVERFLOW;
     }
     return P25CU_OK;
+}
+
+extern "C" int p25cu_poll_view(p25cu_ctx* ctx, const p25cu_event** events, size_t* n) {
+    if (!ctx || !events || !n) return P25CU_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    unsigned total = 0;
+    const int rc = drain(ctx, &total);
+    *events = ctx->h_events;
+    *n = total;
+    return rc;
+}
+
+extern "C" int p25cu_poll(p25cu_ctx* ctx, p25cu_event* out, size_t cap, size_t* n) {
+    if (!ctx || !n || (!out && cap)) return P25CU_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    unsigned total = 0;
+    const int rc = drain(ctx, &total);
+    if (rc != P25CU_OK && rc != P25CU_ERR_OVERFLOW) return rc;
+    const size_t take = total < cap ? total : cap;
+    if (take) memcpy(out, ctx->h_events, take * sizeof(p25cu_event));
+    *n = take;
+    if (take < total) {
+        snprintf(ctx->err, sizeof ctx->err, "event overflow: %u queued, %zu returned (cap too small)", total, take);
+        return P25CU_ERR_OVERFLOW;
+    }
+    return rc;
 }
 
 extern "C" int p25cu_resync(p25cu_ctx* ctx, uint32_t stream) {
@@ -328,8 +409,8 @@ extern "C" int p25cu_resync(p25cu_ctx* ctx, uint32_t stream) {
     CK(cudaSetDevice(ctx->cfg.device));
     const unsigned one = 1;
     CK(cudaMemcpyAsync((char*)(ctx->d_states + stream) + offsetof(WalkState, resync_req), &one, sizeof one,
-                       cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+                       cudaMemcpyHostToDevice, ctx->stream2));
+    CK(cudaStreamSynchronize(ctx->stream2));
     return P25CU_OK;
 }
 
@@ -338,9 +419,9 @@ extern "C" int p25cu_get_stats(p25cu_ctx* ctx, uint32_t stream, p25cu_stats* out
     CK(cudaSetDevice(ctx->cfg.device));
     unsigned raw[P25CU_ST_FAMILIES * 3];
     unsigned* src = ctx->d_stats + (size_t)stream * P25CU_ST_FAMILIES * 3;
-    CK(cudaMemcpyAsync(raw, src, sizeof raw, cudaMemcpyDeviceToHost, ctx->stream));
-    if (clear) CK(cudaMemsetAsync(src, 0, sizeof raw, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(raw, src, sizeof raw, cudaMemcpyDeviceToHost, ctx->stream2));
+    if (clear) CK(cudaMemsetAsync(src, 0, sizeof raw, ctx->stream2));
+    CK(cudaStreamSynchronize(ctx->stream2));
     for (int f = 0; f < P25CU_ST_FAMILIES; f++) {
         out->code[f].words = raw[3 * f];
         out->code[f].errs = raw[3 * f + 1];
@@ -356,12 +437,21 @@ extern "C" int p25cu_sync(p25cu_ctx* ctx) {
     if (!ctx) return P25CU_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream2));
+    return P25CU_OK;
+}
+extern "C" int p25cu_set_overlap(p25cu_ctx* ctx, int on) {
+    if (!ctx) return P25CU_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream2));
+    ctx->overlap = on ? 1 : 0;
     return P25CU_OK;
 }
 extern "C" uint64_t p25cu_launch_count(const p25cu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int p25cu_device_baseband(p25cu_ctx* ctx, const float** ptr, size_t* row_stride, size_t* n_out) {
     if (!ctx || !ptr) return P25CU_ERR_ARG;
-    *ptr = ctx->d_bb + P25CU_BB_HIST;
+    *ptr = ctx->d_bb[ctx->bb_last] + P25CU_BB_HIST;
     if (row_stride) *row_stride = ctx->row_stride;
     if (n_out) *n_out = ctx->last_n_out;
     return P25CU_OK;

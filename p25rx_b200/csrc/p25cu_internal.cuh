@@ -12,13 +12,13 @@
 //   iq chunk      [S][n]            cf32 (8 B) or u8 pairs (2 B), stream-major (caller's layout)
 //   iq tail       2 x [S][HT]       cf32, last HT input samples of every stream (ping-pong)
 //   baseband      [S][row_stride]   f32; row = 256-sample history | this chunk's samples
-//   walker state  [S]               WalkState, one 944 B record per stream
+//   walker state  [S]               WalkState, one 1024 B record per stream
 //   event slots   [S][ev_cap]       p25cu_event (80 B); per-stream fill counts in WalkState
 //   event dense   [sum counts]      compacted (stream, sample)-ordered copy for the host
 //   stats         [S][12][3]        u32 words / errs / fixed
 // ---------------------------------------------------------------------------
 #define P25CU_BB_HIST 256          // baseband history kept in front of every row (>= 231 + lock margin)
-#define P25CU_WALK_WARPS 4         // streams (warps) per walker CTA
+#define P25CU_WALK_WARPS 2         // streams (warps) per walker CTA: small enough to co-reside with 3 ddc_fm CTAs per SM
 
 enum { WS_SYNC = 0, WS_NID = 1, WS_PAYLOAD = 2, WS_FLUSH = 3 };
 
@@ -35,6 +35,7 @@ struct __align__(16) WalkState {
     unsigned overflow;
     unsigned resync_req;          // set by p25cu_resync, honoured at the next chunk
     unsigned char hex[40];
+    unsigned char scratch[64];    // decoder work area (syndromes, Viterbi survivors); not carried state
     unsigned char buf[840];       // data dibits of the unit being received (one per byte)
 };
 static_assert(sizeof(WalkState) % 16 == 0, "WalkState must be a multiple of 16 bytes");
@@ -50,7 +51,7 @@ struct WalkParams {
     unsigned ev_cap;              // slots per stream
     unsigned* stats;              // [S][12][3]
     const P25DevTables* tables;
-    float* bb_rw;                 // same rows, writable (history roll at the end of the chunk)
+    float* bb_next;               // rows the NEXT chunk will be decoded from: receives the 256-sample history
 };
 
 struct DdcParams {

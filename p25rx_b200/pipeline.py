@@ -99,9 +99,17 @@ class Context:
         self._ck(self._L.p25cu_pending(self._h, C.byref(n)))
         return n.value
 
-    def poll(self, cap: int | None = None) -> np.ndarray:
+    def poll(self, cap: int | None = None, copy: bool = True) -> np.ndarray:
+        """Drain queued events ordered by (stream, sample).  copy=False returns a view of the context's
+        pinned buffer (p25cu_poll_view), valid until the next poll."""
         if cap is None:
-            cap = self.pending()
+            ptr, n = C.c_void_p(), C.c_size_t(0)
+            self._ck(self._L.p25cu_poll_view(self._h, C.byref(ptr), C.byref(n)))
+            if n.value == 0:
+                return np.zeros(0, dtype=EVENT_DTYPE)
+            buf = (C.c_char * (n.value * EVENT_DTYPE.itemsize)).from_address(ptr.value)
+            view = np.frombuffer(buf, dtype=EVENT_DTYPE, count=n.value)
+            return view.copy() if copy else view
         ev = np.zeros(max(cap, 1), dtype=EVENT_DTYPE)
         n = C.c_size_t(0)
         self._ck(self._L.p25cu_poll(self._h, ev.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
@@ -117,6 +125,9 @@ class Context:
 
     def sync(self):
         self._ck(self._L.p25cu_sync(self._h))
+
+    def set_overlap(self, on: bool):
+        self._ck(self._L.p25cu_set_overlap(self._h, int(on)))
 
     @property
     def cuda_stream(self) -> int:
