@@ -288,7 +288,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "kernels": {"p25_ddc_fm_kernel_ms": ddc_ms, "step_ms": dev_ms / K, "host_enqueue_ms_per_step": enqueue_ms / K,
                         "serialised": {"p25_ddc_fm_kernel_ms": ddc_serial_ms, "p25_walk_kernel_ms": walk_ms}},
-            "roofline": {"kernel": "p25_ddc_fm_kernel<front=/10, cf32>", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "fast::p25_ddc_fm_stream_kernel (cf32, /50)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": sampler.result(), "events_checked": {"tsbk": n_tsbk, "errors": n_err}}

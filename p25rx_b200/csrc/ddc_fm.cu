@@ -53,37 +53,58 @@ struct Smem {
     float c_re[C::RING], c_im[C::RING];      // channel filter output ring
     float d[C::RING];                        // discriminator output ring
     float red[32];
+    float lut[256];                          // u8 -> f32 table (a per-lane index into __constant__ memory would serialise)
 };
 
-__device__ __forceinline__ float2 cf_from_u8(uchar2 b) { return make_float2(c_iq_lut[b.x], c_iq_lut[b.y]); }
+// The carried input tail is kept in the stream's own sample format (u8 pairs or cf32).  Samples in front of
+// the stream start (absolute index < 0) are zeros: for cf32 the zero-initialised tail says so by itself, for
+// u8 (where no byte maps to 0.0) the rule is explicit: logical index l < ht - a0 is zero.
+template <int FMT>
+struct Elem { using T = float2; };
+template <>
+struct Elem<P25CU_FMT_U8_IQ> { using T = uchar2; };
+
+template <int FMT>
+__device__ __forceinline__ float2 cvt(const float* lut, typename Elem<FMT>::T v) {
+    if constexpr (FMT == P25CU_FMT_CF32_IQ) return v;
+    else return make_float2(lut[v.x], lut[v.y]);
+}
 
 // logical input sample l (0 .. HT+n): tail of the previous chunk, then this chunk; zeros beyond
 template <int FMT>
-__device__ __forceinline__ float2 load_logical(const DdcParams& p, const float2* tail, const void* chunk, long long l) {
-    if (l < (long long)p.ht) return tail[l];
+__device__ __forceinline__ typename Elem<FMT>::T load_logical_raw(const DdcParams& p, const void* tail, const void* chunk, long long l) {
+    using T = typename Elem<FMT>::T;
+    if (l < (long long)p.ht) return ((const T*)tail)[l];
     const long long i = l - p.ht;
-    if (i >= (long long)p.n) return make_float2(0.f, 0.f);
-    if (FMT == P25CU_FMT_CF32_IQ) return __ldcs((const float2*)chunk + i);
-    return cf_from_u8(__ldcs((const uchar2*)chunk + i));
+    if (i >= (long long)p.n) return T{};
+    return __ldcs((const T*)chunk + i);
 }
 
 // Stage logical samples [l0, l0 + XN) into sm.xs.  Global loads are 16 bytes wide and aligned to the
 // *source* (2 cf32 samples or 8 u8 samples per load); each sample is then stored to its own slot, so
 // any decimator phase / chunk parity takes the vector path as long as the rows themselves are aligned.
 template <bool FRONT, int FMT>
-__device__ __forceinline__ void stage_block(Smem<FRONT>& sm, const DdcParams& p, const float2* tail, const void* chunk,
+__device__ __forceinline__ void stage_block(Smem<FRONT>& sm, const DdcParams& p, const void* tail, const void* chunk,
                                             long long l0) {
     using C = Cfg<FRONT>;
     const long long ht = (long long)p.ht;
     const int tid = threadIdx.x;
-    // part 1: samples that still come from the previous chunk's tail (cf32, HT is even)
+    // part 1: samples that still come from the previous chunk's tail (HT is even)
     const long long t_end = l0 + C::XN < ht ? l0 + C::XN : ht;
     if (l0 < t_end) {
-        for (long long l = (l0 & ~1LL) + 2 * tid; l < t_end; l += 2 * C::NT) {
-            const float4 v = *(const float4*)(tail + l);
-            const long long i = l - l0;
-            if (i >= 0) sm.xs[i] = make_float2(v.x, v.y);
-            if (i + 1 < C::XN && l + 1 < t_end) sm.xs[i + 1] = make_float2(v.z, v.w);
+        if constexpr (FMT == P25CU_FMT_CF32_IQ) {
+            for (long long l = (l0 & ~1LL) + 2 * tid; l < t_end; l += 2 * C::NT) {
+                const float4 v = *(const float4*)((const float2*)tail + l);
+                const long long i = l - l0;
+                if (i >= 0) sm.xs[i] = make_float2(v.x, v.y);
+                if (i + 1 < C::XN && l + 1 < t_end) sm.xs[i + 1] = make_float2(v.z, v.w);
+            }
+        } else {
+            const long long zero_below = ht - (long long)p.a0;   // logical indices in front of the stream start
+            for (long long l = l0 + tid; l < t_end; l += C::NT) {
+                const uchar2 b = ((const uchar2*)tail)[l];
+                sm.xs[l - l0] = l < zero_below ? make_float2(0.f, 0.f) : make_float2(sm.lut[b.x], sm.lut[b.y]);
+            }
         }
     }
     // part 2: samples of this chunk (zeros past its end)
@@ -107,7 +128,7 @@ __device__ __forceinline__ void stage_block(Smem<FRONT>& sm, const DdcParams& p,
                     const long long jj = g + e;
                     if (jj >= c_beg && jj < c_end) {
                         const unsigned b = w[e >> 1] >> (16 * (e & 1));
-                        sm.xs[jj + base] = jj < n ? make_float2(c_iq_lut[b & 0xFF], c_iq_lut[(b >> 8) & 0xFF]) : make_float2(0.f, 0.f);
+                        sm.xs[jj + base] = jj < n ? make_float2(sm.lut[b & 0xFF], sm.lut[(b >> 8) & 0xFF]) : make_float2(0.f, 0.f);
                     }
                 }
             }
@@ -115,7 +136,7 @@ __device__ __forceinline__ void stage_block(Smem<FRONT>& sm, const DdcParams& p,
     } else {
         for (long long jj = c_beg + tid; jj < c_end; jj += C::NT) {
             float2 v = make_float2(0.f, 0.f);
-            if (jj < n) v = (FMT == P25CU_FMT_CF32_IQ) ? __ldcs((const float2*)chunk + jj) : cf_from_u8(__ldcs((const uchar2*)chunk + jj));
+            if (jj < n) v = cvt<FMT>(sm.lut, __ldcs((const typename Elem<FMT>::T*)chunk + jj));
             sm.xs[jj + base] = v;
         }
     }
@@ -148,11 +169,13 @@ __global__ void __launch_bounds__(Cfg<FRONT>::NT) p25_ddc_fm_kernel(const DdcPar
     // zero rings and partial buffers (everything behind xs)
     {
         float* z = reinterpret_cast<float*>(&sm.pa[0][0][0]);
-        const int nz = (int)((sizeof(Smem<FRONT>) - sizeof(sm.xs)) / sizeof(float));
+        const int nz = (int)((sizeof(Smem<FRONT>) - sizeof(sm.xs) - sizeof(sm.lut)) / sizeof(float));
         for (int i = tid; i < nz; i += C::NT) z[i] = 0.f;
+        for (int i = tid; i < 256; i += C::NT) sm.lut[i] = c_iq_lut[i];
     }
 
-    const float2* tail = p.tail_in + (size_t)s * p.ht;
+    using ET = typename Elem<FMT>::T;
+    const void* tail = (const ET*)p.tail_in + (size_t)s * p.ht;
     const void* chunk = (FMT == P25CU_FMT_CF32_IQ) ? (const void*)((const float2*)p.iq + (size_t)s * p.n)
                                                     : (const void*)((const uchar2*)p.iq + (size_t)s * p.n);
     float* out = p.bb + (size_t)s * p.row_stride + P25CU_BB_HIST;
@@ -288,8 +311,8 @@ __global__ void __launch_bounds__(Cfg<FRONT>::NT) p25_ddc_fm_kernel(const DdcPar
 
     // the last segment of each stream writes the input tail for the next chunk
     if (g == p.n_seg - 1) {
-        float2* tout = p.tail_out + (size_t)s * p.ht;
-        for (int i = tid; i < (int)p.ht; i += C::NT) tout[i] = load_logical<FMT>(p, tail, chunk, (long long)p.n + i);
+        ET* tout = (ET*)p.tail_out + (size_t)s * p.ht;
+        for (int i = tid; i < (int)p.ht; i += C::NT) tout[i] = load_logical_raw<FMT>(p, tail, chunk, (long long)p.n + i);
     }
 }
 
@@ -407,7 +430,7 @@ __global__ void __launch_bounds__(NT, 3) p25_ddc_fm_stream_kernel(const DdcParam
         unsigned it1 = blocks_per_stream;
         if (b_end - b < (unsigned long long)(it1 - it0)) it1 = it0 + (unsigned)(b_end - b);
         b += it1 - it0;
-        const float2* tail = p.tail_in + (size_t)s * p.ht;
+        const float2* tail = (const float2*)p.tail_in + (size_t)s * p.ht;
         const float2* chunk = (const float2*)p.iq + (size_t)s * p.n;
         const long long mb = M0 + (long long)it0 * MB;
         long long me = M0 + (long long)it1 * MB;
@@ -544,15 +567,309 @@ __global__ void __launch_bounds__(NT, 3) p25_ddc_fm_stream_kernel(const DdcParam
             }
         }
         if (it1 == blocks_per_stream) {   // this piece ends the stream's chunk: write the tail for the next chunk
-            float2* tout = p.tail_out + (size_t)s * p.ht;
+            float2* tout = (float2*)p.tail_out + (size_t)s * p.ht;
             for (int i = tid; i < (int)p.ht; i += NT)
-                tout[i] = load_logical<P25CU_FMT_CF32_IQ>(p, tail, chunk, (long long)p.n + i);
+                tout[i] = load_logical_raw<P25CU_FMT_CF32_IQ>(p, tail, chunk, (long long)p.n + i);
         }
         __syncthreads();
     }
 }
 
 }  // namespace fast
+
+
+// =====================================================================================================
+// Fast path for the reference's own chain (/5 from 240 kS/s; u8 or cf32 input; 16-byte aligned rows).
+// At 2.8 bytes per input sample the FP32 pipe, not HBM, is the first limit of this shape (66 complex-by-
+// real taps per 48 kHz output), so the kernel is organised around issue slots:
+//   * tiles of MB outputs are independent: a tile recomputes its own 50-output warm-up (40 channel-filter
+//     taps + discriminator + boxcar) from raw input, so there is no carried on-chip state and every CTA of
+//     the persistent grid simply walks its share of the flattened (stream, tile) space;
+//   * the raw tile (u8 pairs or cf32) is staged by TMA 1-D bulk copies into a two-stage ring;
+//   * decimator: a thread owns 5R consecutive inputs, converts them once (u8: PRMT into the mantissa of
+//     2^23, one packed add) and forms its R outputs' own part plus the part it contributes to its left
+//     neighbour's last four outputs; neighbours exchange by warp shuffle (lane 31 of a warp is a ghost whose
+//     outputs belong to lane 0 of the next warp).  25 FFMA2 per output, no redundant conversion;
+//   * channel filter: 6 outputs per thread from a sliding register window (23 LDS.128 per 246 FFMA2);
+//   * u8 samples stay in byte units, centred on 128: the discriminator is scale-invariant, the remaining
+//     DC of (0.5 / 127.5) is added back as the channel filter's initial accumulator, power is rescaled.
+// =====================================================================================================
+namespace fast5 {
+
+using fast::cfma;
+using fast::mbar_init;
+using fast::mbar_expect_tx;
+using fast::mbar_wait;
+using fast::tma_load_1d;
+
+template <int FMT>
+struct K {
+    static constexpr bool U8 = FMT == P25CU_FMT_U8_IQ;
+    static constexpr int NW = 6, NT = 32 * NW;
+    static constexpr int R = U8 ? 4 : 5;                       // decimator outputs per thread
+    static constexpr int NYD = NW * 31 * R;                    // decimator outputs per tile
+    static constexpr int HC = P25_TAPS_CHAN - 1;               // 40
+    static constexpr int HALO = HC + 1 + (P25_BOXCAR - 1);     // 50 warm-up outputs
+    static constexpr int MB = NYD - HALO;                      // stored outputs per tile
+    static constexpr int XN = 5 * NYD + 5 * R;                 // input samples read per tile (incl. the last ghost lane)
+    static constexpr int AL = U8 ? 8 : 2;                      // samples per 16 bytes
+    static constexpr int ES = U8 ? 2 : 8;                      // bytes per sample
+    static constexpr int XLEN = (XN + 2 * AL - 2) / AL * AL;   // staged samples: XN + alignment skew, whole 16-byte groups
+    static constexpr int XBYTES = (XLEN * ES + 127) / 128 * 128;
+    static constexpr int RC = 6;                               // channel-filter outputs per thread
+    static constexpr int NC = NYD - HC;                        // channel-filter outputs per tile
+    static constexpr int NCT = (NC + RC - 1) / RC;             // threads busy in the channel filter
+    static constexpr int ND = NC - 1;                          // discriminator outputs per tile
+    static_assert(MB % 2 == 0 && (R % 2 == 0 || !U8), "pair stores / word-aligned u8 columns");
+    static_assert(NCT <= NT, "channel filter must fit one pass");
+};
+
+template <int FMT>
+struct __align__(128) Smem {
+    using C = K<FMT>;
+    unsigned char xs[2][C::XBYTES];      // TMA destinations (raw samples)
+    float2 yd[C::NCT * C::RC + C::HC + 2];   // decimator outputs (padded for the last channel-filter thread)
+    float2 c[C::NCT * C::RC + 6];
+    float d[C::ND + 20];
+    unsigned long long full[2];
+};
+
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+
+// atan2 for the discriminator: |error| <= 2e-7 rad (degree-7 minimax in t^2 on [0, 1], spec/gen_tables.py
+// style fit; CUDA's atan2f costs ~85 instructions with its special-case branches, this one ~22, branch-free).
+// atan2(0, 0) = 0 like std::atan2 on +0 arguments.
+__device__ __forceinline__ float disc_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaxf(mx, 1e-30f)));
+    const float t = mn * rc, u = t * t;
+    float q = -0.004295386839658022f;
+    q = fmaf(q, u, 0.022737378254532814f);
+    q = fmaf(q, u, -0.057179518043994904f);
+    q = fmaf(q, u, 0.09735459089279175f);
+    q = fmaf(q, u, -0.13945257663726807f);
+    q = fmaf(q, u, 0.1995391547679901f);
+    q = fmaf(q, u, -0.3333050608634949f);
+    q = fmaf(q, u, 0.9999995231628418f);
+    float r = q * t;
+    r = ay > ax ? 1.57079632679489662f - r : r;
+    r = x < 0.f ? 3.14159265358979324f - r : r;
+    return copysignf(r, y);
+}
+
+// 5R u8 samples starting at half-word ODD of wp[0] -> floats in byte units centred on 128
+template <int R, bool ODD>
+__device__ __forceinline__ void load_u8(const unsigned* __restrict__ wp, float2 (&x)[5 * R]) {
+    constexpr int NWORD = (5 * R + (ODD ? 1 : 0) + 1) / 2;
+    unsigned w[NWORD];
+#pragma unroll
+    for (int i = 0; i < NWORD; i++) w[i] = wp[i];
+    const float2 off = make_float2(-8388736.f, -8388736.f);   // -(2^23 + 128)
+#pragma unroll
+    for (int i = 0; i < 5 * R; i++) {
+        const int hw = i + (ODD ? 1 : 0);
+        const unsigned word = w[hw >> 1];
+        // bytes {b, 0, 0, 0x4B}: the float 2^23 + b
+        const unsigned fi = __byte_perm(word, 0x4B000000u, (hw & 1) ? 0x7442u : 0x7440u);
+        const unsigned fq = __byte_perm(word, 0x4B000000u, (hw & 1) ? 0x7443u : 0x7441u);
+        x[i] = add2(make_float2(__uint_as_float(fi), __uint_as_float(fq)), off);
+    }
+}
+
+// bulk copies of logical samples [l0 - skew, ...) covering the tile's window into xs[stage]
+template <int FMT>
+__device__ __forceinline__ void issue_tile(Smem<FMT>& sm, int stage, const DdcParams& p, const unsigned char* tail,
+                                           const unsigned char* chunk, int l0) {
+    using C = K<FMT>;
+    const long long ht = p.ht, lend = ht + (long long)p.n;
+    const long long la = (long long)(l0 & ~(C::AL - 1));
+    long long lb = la + C::XLEN;
+    if (lb > lend) lb = lend;
+    const long long t1 = lb < ht ? lb : ht;
+    const unsigned nt = la < t1 ? (unsigned)(t1 - la) : 0u;     // samples served by the tail
+    const long long cb = la > ht ? la : ht;
+    const unsigned nc = cb < lb ? (unsigned)(lb - cb) : 0u;     // samples served by the chunk
+    mbar_expect_tx(&sm.full[stage], (nt + nc) * C::ES);
+    if (nt) tma_load_1d(&sm.xs[stage][0], tail + la * C::ES, nt * C::ES, &sm.full[stage]);
+    if (nc) tma_load_1d(&sm.xs[stage][(cb - la) * C::ES], chunk + (cb - ht) * C::ES, nc * C::ES, &sm.full[stage]);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(K<FMT>::NT) p25_ddc5_fm_kernel(const DdcParams p, const unsigned tiles_per_stream,
+                                                                   const float dc, const float pw_scale) {
+    using C = K<FMT>;
+    constexpr int R = C::R;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem<FMT>& sm = *reinterpret_cast<Smem<FMT>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // this CTA's share of the flattened (stream, tile) space; (s, it) advance incrementally
+    const unsigned long long total = (unsigned long long)p.n_streams * tiles_per_stream;
+    const unsigned long long b0 = total * blockIdx.x / gridDim.x;
+    const unsigned n_tiles = (unsigned)(total * (blockIdx.x + 1ull) / gridDim.x - b0);
+    const int M0n = (int)p.n_out;
+    const size_t row_bytes = (size_t)p.n * C::ES, tail_bytes = (size_t)p.ht * C::ES;
+    const unsigned char* const iq8 = (const unsigned char*)p.iq;
+    const unsigned char* const tail8 = (const unsigned char*)p.tail_in;
+    // logical index (tail ++ chunk) of the first input of tile `it`: absolute input 5 * (m_lo - HALO) - 20
+    const int l_base = (int)(5 * (long long)p.m0 - (long long)p.a0) - 5 * C::HALO - 20 + (int)p.ht;
+    auto tile_l0 = [&](unsigned it) { return l_base + 5 * C::MB * (int)it; };
+    unsigned s = (unsigned)(b0 / tiles_per_stream), it = (unsigned)(b0 % tiles_per_stream);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned s2 = s, it2 = it;
+        for (unsigned k = 0; k < 2 && k < n_tiles; k++) {
+            issue_tile<FMT>(sm, (int)k, p, tail8 + s2 * tail_bytes, iq8 + s2 * row_bytes, tile_l0(it2));
+            if (++it2 == tiles_per_stream) it2 = 0, s2++;
+        }
+    }
+
+    for (unsigned use = 0; use < n_tiles; use++) {
+        const int stage = use & 1;
+        const int l0 = tile_l0(it);
+        const int skew = l0 & (C::AL - 1);
+        const int m_rel = C::MB * (int)it;                            // first stored output of this tile, relative to m0
+        const int nv = min(M0n - m_rel, C::MB);                       // stored outputs of this tile
+        mbar_wait(&sm.full[stage], (use >> 1) & 1);
+
+        // ---- /5 decimator: column tq owns inputs [5R*tq, 5R*tq + 5R) of the window
+        {
+            const int tq = warp * 31 + lane;
+            float2 x[5 * R];
+            if constexpr (C::U8) {
+                const int s0 = skew + 5 * R * tq;
+                const unsigned* wp = reinterpret_cast<const unsigned*>(sm.xs[stage]) + (s0 >> 1);
+                if (s0 & 1) load_u8<R, true>(wp, x);
+                else load_u8<R, false>(wp, x);
+            } else {
+                const float2* xp = reinterpret_cast<const float2*>(sm.xs[stage]) + skew + 5 * R * tq;
+#pragma unroll
+                for (int i = 0; i < 5 * R; i++) x[i] = xp[i];
+            }
+            float2 own[R], left[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                own[r] = make_float2(0.f, 0.f);
+                left[r] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = P25_TAPS_DECIM - 1; k >= 0; k--) {      // oldest input first
+                    const int idx = 5 * r + (P25_TAPS_DECIM - 1) - k;
+                    if (idx < 5 * R) own[r] = cfma(c_taps_decim[k], x[idx], own[r]);
+                    else left[r] = cfma(c_taps_decim[k], x[idx - 5 * R], left[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (5 * r + (P25_TAPS_DECIM - 1) >= 5 * R) {          // this output reaches into the right neighbour's inputs
+                    const float rx = __shfl_down_sync(0xFFFFFFFFu, left[r].x, 1);
+                    const float ry = __shfl_down_sync(0xFFFFFFFFu, left[r].y, 1);
+                    own[r].x += rx;
+                    own[r].y += ry;
+                }
+            }
+            if (lane < 31) {
+#pragma unroll
+                for (int r = 0; r < R; r++) sm.yd[R * tq + r] = own[r];
+            }
+        }
+        __syncthreads();                                              // S1: xs[stage] consumed, yd complete
+        if (tid == 0 && use + 2 < n_tiles) {
+            unsigned s2 = s, it2 = it + 2;
+            if (it2 >= tiles_per_stream) it2 -= tiles_per_stream, s2++;
+            if (it2 >= tiles_per_stream) it2 -= tiles_per_stream, s2++;   // tiles_per_stream == 1
+            issue_tile<FMT>(sm, stage, p, tail8 + s2 * tail_bytes, iq8 + s2 * row_bytes, tile_l0(it2));
+        }
+
+        // ---- channel-select FIR: thread computes c[RC*tid .. RC*tid + RC), c[j] = sum_k h[k] * yd[j + 40 - k]
+        if (tid < C::NCT) {
+            float2 acc[C::RC];
+#pragma unroll
+            for (int r = 0; r < C::RC; r++) acc[r] = make_float2(dc, dc);
+            const float4* src = reinterpret_cast<const float4*>(&sm.yd[C::RC * tid]);
+#pragma unroll
+            for (int i = 0; i < (C::HC + C::RC) / 2; i++) {
+                const float4 v = src[i];
+                const float2 xa = make_float2(v.x, v.y), xb = make_float2(v.z, v.w);
+#pragma unroll
+                for (int r = 0; r < C::RC; r++) {
+                    const int ka = C::HC - 2 * i + r, kb = ka - 1;
+                    if (ka >= 0 && ka <= C::HC) acc[r] = cfma(c_taps_chan[ka], xa, acc[r]);
+                    if (kb >= 0 && kb <= C::HC) acc[r] = cfma(c_taps_chan[kb], xb, acc[r]);
+                }
+            }
+            float4* dst = reinterpret_cast<float4*>(&sm.c[C::RC * tid]);
+#pragma unroll
+            for (int r = 0; r < C::RC / 2; r++) dst[r] = make_float4(acc[2 * r].x, acc[2 * r].y, acc[2 * r + 1].x, acc[2 * r + 1].y);
+        }
+        __syncthreads();                                              // S2
+
+        // ---- FM discriminator, 4 per thread: d[j] from c[j + 1], c[j]; c[j] is output m_lo - 10 + j
+        float pw = 0.f;
+        const bool want_pw = p.power_sum != nullptr;
+        for (int q = tid; q < (C::ND + 3) / 4; q += C::NT) {
+            const int j0 = 4 * q;
+            const float4* src = reinterpret_cast<const float4*>(&sm.c[j0]);
+            const float4 v0 = src[0], v1 = src[1];
+            const float2 c4 = sm.c[j0 + 4];
+            const float2 cc[5] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w), c4};
+            float dd[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float2 prv = cc[i], cur = cc[i + 1];
+                const float re = cur.x * prv.x + cur.y * prv.y;
+                const float im = cur.y * prv.x - cur.x * prv.y;
+                dd[i] = disc_atan2(im, re) * P25_FM_GAIN;
+                const int o = j0 + i + 1 - P25_BOXCAR;                // stored-output index of c[j + 1]
+                if (want_pw && o >= 0 && o < nv) pw += cur.x * cur.x + cur.y * cur.y;
+            }
+            *reinterpret_cast<float4*>(&sm.d[j0]) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+        }
+        __syncthreads();                                              // S3
+
+        // ---- symbol-period boxcar, 4 outputs per thread: out[o] = mean(d[o .. o + 9]), oldest first
+        for (int o0 = 4 * tid; o0 < nv; o0 += 4 * C::NT) {
+            const float4* src = reinterpret_cast<const float4*>(&sm.d[o0]);
+            const float4 a = src[0], b = src[1], c4 = src[2], e = src[3];
+            float s0 = a.x + a.y;
+            s0 += a.z; s0 += a.w; s0 += b.x; s0 += b.y; s0 += b.z; s0 += b.w; s0 += c4.x; s0 += c4.y;
+            const float s1 = (s0 - a.x) + c4.z, s2 = (s1 - a.y) + c4.w, s3 = (s2 - a.z) + e.x;
+            const float k = 1.0f / P25_BOXCAR;
+            float* out = p.bb + (size_t)s * p.row_stride + P25CU_BB_HIST + m_rel + o0;
+            if (o0 + 1 < nv) *reinterpret_cast<float2*>(out) = make_float2(s0 * k, s1 * k);
+            else out[0] = s0 * k;
+            if (o0 + 3 < nv) *reinterpret_cast<float2*>(out + 2) = make_float2(s2 * k, s3 * k);
+            else if (o0 + 2 < nv) out[2] = s2 * k;
+        }
+        if (p.power_sum) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) pw += __shfl_xor_sync(0xFFFFFFFFu, pw, o);
+            if (lane == 0) atomicAdd(p.power_sum + s, pw * pw_scale);
+        }
+        if (it == tiles_per_stream - 1) {   // last tile of the stream's chunk: carry the raw input tail (n >= HT here)
+            const uint4* src = reinterpret_cast<const uint4*>(iq8 + s * row_bytes + ((size_t)p.n - p.ht) * C::ES);
+            uint4* dst = reinterpret_cast<uint4*>((unsigned char*)p.tail_out + s * tail_bytes);
+            for (int i = tid; i < (int)(tail_bytes / 16); i += C::NT) dst[i] = src[i];
+        }
+        // no barrier needed here: the next tile's first shared-memory writes (yd) are two barriers away from
+        // the last reads of yd, and its d / c writes come after S1 / S2 of the next iteration
+        if (++it == tiles_per_stream) it = 0, s++;
+    }
+}
+
+}  // namespace fast5
 
 unsigned p25cu_ddc_tail_len(int decimation) { return decimation == 50 ? Cfg<true>::HT : Cfg<false>::HT; }
 
@@ -597,8 +914,40 @@ static cudaError_t launch_fast(const DdcParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+template <int FMT>
+static cudaError_t launch_fast5(const DdcParams& p, cudaStream_t st) {
+    using C = fast5::K<FMT>;
+    static int grid_cache = 0;
+    auto kern = fast5::p25_ddc5_fm_kernel<FMT>;
+    const size_t smem = sizeof(fast5::Smem<FMT>);
+    if (!grid_cache) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int dev = 0, n_sm = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NT, smem);
+        if (e != cudaSuccess) return e;
+        grid_cache = n_sm * (per_sm > 0 ? per_sm : 1);
+    }
+    const unsigned tps = (p.n_out + C::MB - 1) / C::MB;
+    const unsigned long long total = (unsigned long long)p.n_streams * tps;
+    const unsigned grid = total < (unsigned long long)grid_cache ? (unsigned)total : (unsigned)grid_cache;
+    // u8 samples are processed in byte units centred on 128: x_true = (u + 0.5) / 127.5 (spec iq_lut)
+    double gd = 0.0, gc = 0.0;
+    for (int k = 0; k < P25_TAPS_DECIM; k++) gd += (double)P25_TAPS_DECIM_H[k];
+    for (int k = 0; k < P25_TAPS_CHAN; k++) gc += (double)P25_TAPS_CHAN_H[k];
+    const float dc = C::U8 ? (float)(0.5 * gd * gc) : 0.f;
+    const float pw_scale = C::U8 ? (float)(1.0 / (127.5 * 127.5)) : 1.f;
+    kern<<<grid, C::NT, smem, st>>>(p, tps, dc, pw_scale);
+    return cudaGetLastError();
+}
+
 cudaError_t p25cu_launch_ddc(const DdcParams& p, int format, int decimation, cudaStream_t st) {
     if (p.n_out == 0 && p.n == 0) return cudaSuccess;
+    // /5 fast path: aligned rows, the whole history inside the stream (no implicit zeros), chunk at least one tail long
+    if (decimation == 5 && p.aligned16 && p.n_out > 0 && p.a0 >= p.ht && p.n >= p.ht && p.ht == (unsigned)Cfg<false>::HT)
+        return format == P25CU_FMT_CF32_IQ ? launch_fast5<P25CU_FMT_CF32_IQ>(p, st) : launch_fast5<P25CU_FMT_U8_IQ>(p, st);
     if (decimation == 50 && format == P25CU_FMT_CF32_IQ && p.aligned16 && (p.a0 & 1ull) == 0 && p.n_out > 0 &&
         p.ht == (unsigned)Cfg<true>::HT)
         return launch_fast(p, st);

@@ -56,8 +56,8 @@ struct WalkParams {
 
 struct DdcParams {
     const void* iq;               // chunk, [S][n]
-    const float2* tail_in;        // [S][HT]
-    float2* tail_out;             // [S][HT]
+    const void* tail_in;          // [S][HT] samples in the stream's own format (uchar2 or float2)
+    void* tail_out;               // [S][HT]
     float* bb;                    // baseband rows (outputs start at column P25CU_BB_HIST)
     size_t row_stride;
     float* power_sum;             // [S], atomically accumulated sum |c|^2 of this chunk
