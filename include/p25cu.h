@@ -160,7 +160,8 @@ int p25cu_device_baseband(p25cu_ctx* ctx, const float** ptr, size_t* row_stride,
  *       (uint32 words; out_data uint32, out_nerr int32, -1 = unrecoverable)
  *       7 rs (n,k) on `count` blocks of n bytes, corrected in place in `words`
  *       8 half-rate trellis: `count` blocks of 98 dibit bytes -> 12 bytes each in out_data
- *       9 imbe: `count` blocks of 72 dibit bytes -> 15 uint32 each in out_data */
+ *       9 imbe: `count` blocks of 72 dibit bytes -> 15 uint32 each in out_data
+ *       10..13: the warp-cooperative forms the decode walker uses (one warp per word) of kinds 7, 9, 0, 8 */
 int p25cu_fec_selftest(p25cu_ctx* ctx, int kind, void* words, size_t count, int n, int k,
                        void* out_data, int32_t* out_nerr);
 

@@ -32,6 +32,9 @@ struct WalkShared {
     P25DevTables T;
     WalkState ws[P25CU_WALK_WARPS];
     float win[P25CU_WALK_WARPS][WIN_LEN + 2];
+    alignas(16) unsigned char scr[P25CU_WALK_WARPS][192];   // decoder work area (syndromes, locator, IMBE results)
+    unsigned short pn_a[116], pn_c[116];        // IMBE PN generator n steps ahead: p_n = pn_a[n] * p_0 + pn_c[n] (mod 2^16)
+    unsigned char imbe_src[8 * 24];             // inverse of the IMBE interleave schedule: [code word][bit] -> frame bit
 };
 
 // packed pair of IEEE fused multiply-adds (one FFMA2): each half is exactly fmaf()
@@ -264,6 +267,160 @@ __device__ __noinline__ int warp_trellis_half_decode(const P25DevTables& T, unsi
     return m0;
 }
 
+// Berlekamp-Massey with a run-time syndrome count (one copy for RS(24,12), RS(24,16), RS(36,20)); same recurrence
+// as p25_berlekamp_massey<N>.  Lane 0 only; all arrays in the warp's scratch area.
+__device__ __noinline__ int bm_runtime(const P25DevTables& T, const unsigned char* S, unsigned char* lam, unsigned char* B,
+                                       unsigned char* Tm, int N) {
+    for (int i = 0; i <= N; i++) {
+        lam[i] = 0;
+        B[i] = 0;
+    }
+    lam[0] = 1;
+    B[0] = 1;
+    int L = 0, m = 1, b = 1;
+    for (int r = 0; r < N; r++) {
+        int d = S[r];
+        for (int i = 1; i <= L; i++) d ^= p25_gf_mul(T, lam[i], S[r - i]);
+        if (d == 0) {
+            m++;
+            continue;
+        }
+        const int coef = p25_gf_div(T, d, b);
+        if (2 * L <= r) {
+            for (int i = 0; i <= N; i++) Tm[i] = lam[i];
+            for (int i = 0; i + m <= N; i++) lam[i + m] ^= (unsigned char)p25_gf_mul(T, coef, B[i]);
+            L = r + 1 - L;
+            for (int i = 0; i <= N; i++) B[i] = Tm[i];
+            b = d;
+            m = 1;
+        } else {
+            for (int i = 0; i + m <= N; i++) lam[i + m] ^= (unsigned char)p25_gf_mul(T, coef, B[i]);
+            m++;
+        }
+    }
+    return L;
+}
+
+__device__ __forceinline__ int warp_rs_syndromes(const P25DevTables& T, const unsigned char* sym, int n, int nroots, int lane) {
+    int acc = 0;
+    if (lane < nroots) {
+        const int a = T.gf_exp[lane + 1];
+        for (int i = 0; i < n; i++) acc = p25_gf_mul(T, acc, a) ^ sym[i];
+    }
+    return acc;
+}
+
+// Reed-Solomon (n, k) over GF(64), all 32 lanes: one syndrome per lane, Berlekamp-Massey on lane 0, Chien search and
+// Forney magnitudes two positions per lane.  Same bounded-distance result (and the same "leave the word as received"
+// on failure) as p25_rs_decode.  sym lives in shared memory; returns corrected symbols or -1, uniformly.
+__device__ __noinline__ int warp_rs_decode(const P25DevTables& T, unsigned char* scr, unsigned char* sym, int n, int k, int lane) {
+    const int nroots = n - k, t = nroots >> 1;
+    unsigned char *S = scr, *lam = scr + 16, *omega = scr + 40, *dlam = scr + 56, *B = scr + 80, *Tm = scr + 104;
+    {
+        const int acc = warp_rs_syndromes(T, sym, n, nroots, lane);
+        if (!__ballot_sync(FULL, acc != 0)) return 0;
+        if (lane < nroots) S[lane] = (unsigned char)acc;
+    }
+    __syncwarp();
+    int L = 0;
+    if (lane == 0) L = bm_runtime(T, S, lam, B, Tm, nroots);
+    L = __shfl_sync(FULL, L, 0);
+    if (L > t) return -1;
+    __syncwarp();
+    if (lane < nroots) {
+        int acc = 0;
+        for (int j = 0; j <= lane && j <= L; j++) acc ^= p25_gf_mul(T, lam[j], S[lane - j]);
+        omega[lane] = (unsigned char)acc;
+    }
+    if (lane < 17) dlam[lane] = (lane + 1 <= L && !(lane & 1)) ? lam[lane + 1] : 0;   // formal derivative: odd terms shift down
+    __syncwarp();
+    bool bad = false, isroot[2];
+    int loc[2] = {0, 0}, mag[2] = {0, 0};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int p = lane + 32 * h;
+        const int xinv = T.gf_exp[(63 - p) % 63];
+        isroot[h] = p < 63 && p25_poly_eval(T, lam, L, xinv) == 0;
+        if (isroot[h]) {
+            if (p >= n) {
+                bad = true;
+            } else {
+                const int den = p25_poly_eval(T, dlam, L > 0 ? L - 1 : 0, xinv);
+                const int mg = den ? p25_gf_div(T, p25_poly_eval(T, omega, nroots - 1, xinv), den) : 0;
+                if (den == 0 || mg == 0) bad = true;
+                loc[h] = n - 1 - p;
+                mag[h] = mg;
+            }
+        }
+    }
+    const int roots = __popc(__ballot_sync(FULL, isroot[0])) + __popc(__ballot_sync(FULL, isroot[1]));
+    if (__any_sync(FULL, bad) || roots != L) return -1;
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+        if (isroot[h]) sym[loc[h]] ^= (unsigned char)mag[h];
+    __syncwarp();
+    if (__ballot_sync(FULL, warp_rs_syndromes(T, sym, n, nroots, lane) != 0)) {
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+            if (isroot[h]) sym[loc[h]] ^= (unsigned char)mag[h];   // leave the word as received
+        __syncwarp();
+        return -1;
+    }
+    return L;
+}
+
+// IMBE voice frame by the whole warp: four lanes gather each code word through the inverse interleave schedule,
+// the PN mask bits come from the generator's closed form n steps ahead, and the seven code words are decoded side
+// by side (lane group c owns c_c).  out15 (shared memory) receives u0..u7 and the 7 corrected-bit counts, exactly
+// the output of p25_imbe_decode.
+__device__ __noinline__ void warp_imbe_decode(const WalkShared& sh, const unsigned char* dibits, int lane, unsigned* out15) {
+    const P25DevTables& T = sh.T;
+    const int c = lane >> 2, q = lane & 3;
+    const int nb = c < 7 ? T.imbe_cw_bits[c] : 7;
+    unsigned v = 0;
+    for (int b = q; b < nb; b += 4) {
+        const int i = sh.imbe_src[c * 24 + b];
+        v |= ((dibits[i >> 1] >> (1 - (i & 1))) & 1u) << b;
+    }
+    v |= __shfl_xor_sync(FULL, v, 1);
+    v |= __shfl_xor_sync(FULL, v, 2);
+    unsigned u0 = 0;
+    const int e0 = p25_golay23_decode(T, v, &u0);   // meaningful on group 0
+    u0 = __shfl_sync(FULL, u0, 0);
+    const unsigned p0 = (16u * u0) & 0xFFFF;
+    // PN bits of code word c start after those of code words 1 .. c-1 (23, 23, 23, 15, 15, 15 bits)
+    const int off = c <= 4 ? 23 * (c - 1) : 69 + 15 * (c - 4);
+    unsigned mask = 0;
+    if (c >= 1 && c <= 6) {
+        for (int j = q; j < nb; j += 4) {
+            const int n = off + 1 + j;
+            const unsigned pn = (sh.pn_a[n] * p0 + sh.pn_c[n]) & 0xFFFF;
+            mask |= (pn >> 15) << (nb - 1 - j);
+        }
+    }
+    mask |= __shfl_xor_sync(FULL, mask, 1);
+    mask |= __shfl_xor_sync(FULL, mask, 2);
+    const unsigned w = v ^ mask;
+    unsigned dg = 0, dh = 0;
+    const int eg = p25_golay23_decode(T, w, &dg), eh = p25_hamming15_decode(T, w, &dh);
+    if (q == 0) {
+        if (c == 0) {
+            out15[0] = u0;
+            out15[8] = (unsigned)e0;
+        } else if (c < 4) {
+            out15[c] = dg;
+            out15[8 + c] = (unsigned)eg;
+        } else if (c < 7) {
+            out15[c] = dh;
+            out15[8 + c] = (unsigned)eh;
+        } else {
+            out15[7] = v & 0x7F;
+        }
+    }
+    __syncwarp();
+}
+
 // TSBK block decoded by the warp (reference src/recv.rs:231); lane 0 applies the result.
 __device__ __forceinline__ void tsbk_apply(const WarpCtx& c, unsigned long long idx, int fixed, const unsigned char* out) {
     WalkState& ws = *c.ws;
@@ -279,113 +436,155 @@ __device__ __forceinline__ void tsbk_apply(const WarpCtx& c, unsigned long long 
     emit(c, P25CU_EV_TSBK, idx, out, 12);
 }
 
-// A payload decision point has been reached (ws.cnt == target).
-__device__ __noinline__ void complete_payload(const WarpCtx& c, unsigned long long idx) {
+// lane 0 adds a batch of code-word outcomes to a stats family (n words, `bad` of them uncorrectable, `fixed` bits)
+__device__ __forceinline__ void stat_batch(const WarpCtx& c, int fam, unsigned n, unsigned bad, unsigned fixed) {
+    unsigned* s = c.p->stats + ((size_t)c.stream * P25CU_ST_FAMILIES + fam) * 3;
+    s[0] += n;
+    s[1] += bad;
+    s[2] += fixed;
+}
+
+// A payload decision point has been reached (ws.cnt == target).  Called by the whole warp: code words of a batch
+// are decoded one per lane, Reed-Solomon and IMBE frames by the warp-cooperative decoders above; lane 0 alone
+// touches the receiver state, the stats and the event slots.
+__device__ __noinline__ void complete_payload(const WarpCtx& c, const WalkShared& sh, unsigned char* scr, unsigned long long idx, int lane) {
     WalkState& ws = *c.ws;
     const P25DevTables& T = *c.T;
-    switch (ws.duid) {
-        case 0x0: {  // HDU -> VoiceHeader (reference src/recv.rs:223)
-            for (int w = 0; w < 36; w++) {
+    const int duid = ws.duid;
+    if (duid == 0x0 || duid == 0xF) {
+        // HDU -> VoiceHeader (reference src/recv.rs:223): 36 x Golay(18,6) + RS(36,20)
+        // TDULC -> VoiceTerm (reference src/recv.rs:232): 12 x Golay(24,12) + RS(24,12)
+        const bool hdu = duid == 0x0;
+        const int nw = hdu ? 36 : 12;
+        unsigned nbad = 0, nfix = 0;
+        for (int w = lane; w < nw; w += 32) {
+            if (hdu) {
                 unsigned d6;
                 const int n = p25_golay18_decode(T, p25_take_bits(ws.buf, 18 * w, 18), &d6);
-                if (n < 0) stat_bad(c, P25CU_ST_GOLAY_SHORT); else stat_ok(c, P25CU_ST_GOLAY_SHORT, (unsigned)n);
+                if (n < 0) nbad++; else nfix += (unsigned)n;
                 ws.hex[w] = (unsigned char)d6;
-            }
-            const int n = p25_rs_decode(T, ws.hex, 36, 20);
-            if (n < 0) {
-                stat_bad(c, P25CU_ST_RS_LONG);
-                fail(c, P25CU_E_RS, idx);
-                return;
-            }
-            stat_ok(c, P25CU_ST_RS_LONG, (unsigned)n);
-            unsigned char out[15];
-            p25_pack_hexbits(ws.hex, 20, out);
-            ws.state = WS_FLUSH;
-            emit(c, P25CU_EV_VOICE_HEADER, idx, out, 15);
-            return;
-        }
-        case 0xF: {  // TDULC -> VoiceTerm (reference src/recv.rs:232)
-            for (int w = 0; w < 12; w++) {
+            } else {
                 unsigned d12;
                 const unsigned word = p25_take_bits(ws.buf, 24 * w, 24);
                 const int n = p25_golay24_decode(T, word, &d12);
                 if (n < 0) {
-                    stat_bad(c, P25CU_ST_GOLAY_EXT);
+                    nbad++;
                     d12 = word >> 12;
                 } else {
-                    stat_ok(c, P25CU_ST_GOLAY_EXT, (unsigned)n);
+                    nfix += (unsigned)n;
                 }
                 ws.hex[2 * w] = (unsigned char)(d12 >> 6);
                 ws.hex[2 * w + 1] = (unsigned char)(d12 & 0x3F);
             }
-            const int n = p25_rs_decode(T, ws.hex, 24, 12);
-            if (n < 0) {
-                stat_bad(c, P25CU_ST_RS_SHORT);
-                fail(c, P25CU_E_RS, idx);
-                return;
-            }
-            stat_ok(c, P25CU_ST_RS_SHORT, (unsigned)n);
-            unsigned char out[9];
-            p25_pack_hexbits(ws.hex, 12, out);
-            ws.state = WS_FLUSH;
-            emit(c, P25CU_EV_VOICE_TERM, idx, out, 9);
-            return;
         }
-        default: {  // LDU1 / LDU2 parts (reference src/recv.rs:224-230)
-            const int kind = T.ldu_kind[ws.part];
-            const unsigned char* d = ws.buf + T.ldu_start[ws.part];
-            ws.part++;
-            if (kind == 0) {
-                unsigned pl[15];
-                p25_imbe_decode(T, d, pl, pl + 8);
-                for (int i = 0; i < 4; i++) stat_ok(c, P25CU_ST_GOLAY_STD, pl[8 + i]);
-                for (int i = 4; i < 7; i++) stat_ok(c, P25CU_ST_HAMMING_STD, pl[8 + i]);
-                if (ws.part == P25_LDU_PARTS) ws.state = WS_FLUSH;
-                emit(c, P25CU_EV_VOICE_FRAME, idx, pl, 60);
-                return;
+        nbad = __reduce_add_sync(FULL, nbad);
+        nfix = __reduce_add_sync(FULL, nfix);
+        __syncwarp();
+        const int n = warp_rs_decode(T, scr, ws.hex, hdu ? 36 : 24, hdu ? 20 : 12, lane);
+        if (lane == 0) {
+            stat_batch(c, hdu ? P25CU_ST_GOLAY_SHORT : P25CU_ST_GOLAY_EXT, (unsigned)nw, nbad, nfix);
+            const int fam = hdu ? P25CU_ST_RS_LONG : P25CU_ST_RS_SHORT;
+            if (n < 0) {
+                stat_bad(c, fam);
+                fail(c, P25CU_E_RS, idx);
+            } else {
+                stat_ok(c, fam, (unsigned)n);
+                unsigned char out[15];
+                p25_pack_hexbits(ws.hex, hdu ? 20 : 12, out);
+                ws.state = WS_FLUSH;
+                emit(c, hdu ? P25CU_EV_VOICE_HEADER : P25CU_EV_VOICE_TERM, idx, out, hdu ? 15 : 9);
             }
-            if (kind == 1) {
-                for (int w = 0; w < 4; w++) {
-                    unsigned d6;
-                    const int n = p25_hamming10_decode(T, p25_take_bits(d, 10 * w, 10), &d6);
-                    if (n < 0) stat_bad(c, P25CU_ST_HAMMING_SHORT); else stat_ok(c, P25CU_ST_HAMMING_SHORT, (unsigned)n);
-                    ws.hex[4 * ws.chunks + w] = (unsigned char)d6;
-                }
-                if (++ws.chunks < 6) return;
-                const bool lc = ws.duid == 0x5;
-                const int n = p25_rs_decode(T, ws.hex, 24, lc ? 12 : 16);
+        }
+        return;
+    }
+    // LDU1 / LDU2 parts (reference src/recv.rs:224-230)
+    const int part = ws.part;
+    const int kind = T.ldu_kind[part];
+    const unsigned char* d = ws.buf + T.ldu_start[part];
+    if (kind == 0) {
+        unsigned* pl = reinterpret_cast<unsigned*>(scr + 128);   // 15 words
+        warp_imbe_decode(sh, d, lane, pl);
+        if (lane == 0) {
+            ws.part = part + 1;
+            stat_batch(c, P25CU_ST_GOLAY_STD, 4, 0, pl[8] + pl[9] + pl[10] + pl[11]);
+            stat_batch(c, P25CU_ST_HAMMING_STD, 3, 0, pl[12] + pl[13] + pl[14]);
+            if (part + 1 == P25_LDU_PARTS) ws.state = WS_FLUSH;
+            emit(c, P25CU_EV_VOICE_FRAME, idx, pl, 60);
+        }
+        return;
+    }
+    if (kind == 1) {
+        const int chunks = ws.chunks;
+        unsigned bad = 0, fix = 0;
+        if (lane < 4) {
+            unsigned d6;
+            const int n = p25_hamming10_decode(T, p25_take_bits(d, 10 * lane, 10), &d6);
+            if (n < 0) bad = 1; else fix = (unsigned)n;
+            ws.hex[4 * chunks + lane] = (unsigned char)d6;
+        }
+        bad = __reduce_add_sync(FULL, bad);
+        fix = __reduce_add_sync(FULL, fix);
+        __syncwarp();
+        const bool lc = duid == 0x5;
+        int n = 0;
+        if (chunks + 1 == 6) n = warp_rs_decode(T, scr, ws.hex, 24, lc ? 12 : 16, lane);
+        if (lane == 0) {
+            ws.part = part + 1;
+            ws.chunks = chunks + 1;
+            stat_batch(c, P25CU_ST_HAMMING_SHORT, 4, bad, fix);
+            if (chunks + 1 == 6) {
+                const int fam = lc ? P25CU_ST_RS_SHORT : P25CU_ST_RS_MED;
                 if (n < 0) {
-                    stat_bad(c, lc ? P25CU_ST_RS_SHORT : P25CU_ST_RS_MED);
+                    stat_bad(c, fam);
                     fail(c, P25CU_E_RS, idx);
-                    return;
+                } else {
+                    stat_ok(c, fam, (unsigned)n);
+                    unsigned char out[12];
+                    p25_pack_hexbits(ws.hex, lc ? 12 : 16, out);
+                    emit(c, lc ? P25CU_EV_LINK_CONTROL : P25CU_EV_CRYPTO_CONTROL, idx, out, lc ? 9 : 12);
                 }
-                stat_ok(c, lc ? P25CU_ST_RS_SHORT : P25CU_ST_RS_MED, (unsigned)n);
-                unsigned char out[12];
-                p25_pack_hexbits(ws.hex, lc ? 12 : 16, out);
-                emit(c, lc ? P25CU_EV_LINK_CONTROL : P25CU_EV_CRYPTO_CONTROL, idx, out, lc ? 9 : 12);
-                return;
             }
-            unsigned frag = 0;
-            for (int w = 0; w < 2; w++) {
-                unsigned d8;
-                const int n = p25_cyclic16_decode(T, p25_take_bits(d, 16 * w, 16), &d8);
-                if (n < 0) stat_bad(c, P25CU_ST_CYCLIC); else stat_ok(c, P25CU_ST_CYCLIC, (unsigned)n);
-                frag = (frag << 8) | d8;
-            }
+        }
+        return;
+    }
+    {   // low-speed data: 2 x cyclic(16,8)
+        unsigned d8 = 0, bad = 0, fix = 0;
+        if (lane < 2) {
+            const int n = p25_cyclic16_decode(T, p25_take_bits(d, 16 * lane, 16), &d8);
+            if (n < 0) bad = 1; else fix = (unsigned)n;
+        }
+        bad = __reduce_add_sync(FULL, bad);
+        fix = __reduce_add_sync(FULL, fix);
+        const unsigned d1 = __shfl_sync(FULL, d8, 1);
+        if (lane == 0) {
+            ws.part = part + 1;
+            stat_batch(c, P25CU_ST_CYCLIC, 2, bad, fix);
+            const unsigned frag = (d8 << 8) | d1;
             emit(c, P25CU_EV_LSD, idx, &frag, 4);
-            return;
         }
     }
 }
 
 // ---------------------------------------------------------------- the walker
+// Stage the decode tables and build the derived ones (callers __syncthreads() before use).
+__device__ __forceinline__ void walk_shared_init(WalkShared& sh, const P25DevTables* tables) {
+    const uint4* src = (const uint4*)tables;
+    uint4* dst = (uint4*)&sh.T;
+    for (unsigned i = threadIdx.x; i < sizeof(P25DevTables) / 16; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) {   // IMBE PN generator n steps ahead: p_n = a_n * p_0 + c_n (mod 2^16), a_n = 173^n
+        unsigned a = 1, cc = 0;
+        for (int n = 0; n < 116; n++) {
+            sh.pn_a[n] = (unsigned short)a;
+            sh.pn_c[n] = (unsigned short)cc;
+            a = (173u * a) & 0xFFFF;
+            cc = (173u * cc + 13849u) & 0xFFFF;
+        }
+    }
+    for (unsigned i = threadIdx.x; i < 144; i += blockDim.x) sh.imbe_src[tables->imbe_cw[i] * 24 + tables->imbe_bit[i]] = (unsigned char)i;
+}
 __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(const WalkParams p) {
     __shared__ WalkShared sh;
-    {
-        const uint4* src = (const uint4*)p.tables;
-        uint4* dst = (uint4*)&sh.T;
-        for (unsigned i = threadIdx.x; i < sizeof(P25DevTables) / 16; i += blockDim.x) dst[i] = src[i];
-    }
+    walk_shared_init(sh, p.tables);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned stream = blockIdx.x * P25CU_WALK_WARPS + warp;
     const bool active = stream < p.n_streams;
@@ -573,14 +772,14 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
                 unsigned long long bits = 0;
                 for (int i = 0; i < P25_NID_DIBITS; i++) bits = (bits << 2) | ws.buf[i];
                 unsigned data = 0;
-                const int nerr = warp_bch_decode(sh.T, ws.scratch, bits >> 1, lane, &data);
+                const int nerr = warp_bch_decode(sh.T, sh.scr[warp], bits >> 1, lane, &data);
                 if (lane == 0) nid_apply(c, idx, nerr, data);
             } else if (ws.duid == 0x7) {
                 unsigned char* out = ws.hex;   // 12-byte result area
-                const int fixed = warp_trellis_half_decode(sh.T, ws.scratch, ws.buf, lane, out);
+                const int fixed = warp_trellis_half_decode(sh.T, sh.scr[warp], ws.buf, lane, out);
                 if (lane == 0) tsbk_apply(c, idx, fixed, out);
             } else {
-                if (lane == 0) complete_payload(c, idx);
+                complete_payload(c, sh, sh.scr[warp], idx, lane);
             }
             __syncwarp();
         }
@@ -716,8 +915,62 @@ __global__ void p25_fec_selftest_kernel(const P25DevTables* tables, void* words,
     }
 }
 
+// The warp-cooperative decoders the walker uses, one warp per word: kinds 10 RS, 11 IMBE, 12 BCH, 13 half-rate trellis
+// (same inputs and outputs as kinds 7, 9, 0, 8).
+__global__ void __launch_bounds__(32 * P25CU_WALK_WARPS) p25_fec_selftest_warp_kernel(const P25DevTables* tables, int kind, void* words,
+                                                                                      size_t count, int n, int k, void* out_data,
+                                                                                      int32_t* out_nerr) {
+    __shared__ WalkShared sh;
+    walk_shared_init(sh, tables);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t i = (size_t)blockIdx.x * P25CU_WALK_WARPS + warp;
+    if (i >= count) return;
+    unsigned char* scr = sh.scr[warp];
+    unsigned char* buf = sh.ws[warp].buf;
+    if (kind == 10) {
+        unsigned char* sym = (unsigned char*)words + i * n;
+        if (lane < n) buf[lane] = sym[lane];
+        if (lane + 32 < n) buf[lane + 32] = sym[lane + 32];
+        __syncwarp();
+        const int r = warp_rs_decode(sh.T, scr, buf, n, k, lane);
+        __syncwarp();
+        if (lane < n) sym[lane] = buf[lane];
+        if (lane + 32 < n) sym[lane + 32] = buf[lane + 32];
+        if (lane == 0) out_nerr[i] = r;
+    } else if (kind == 11) {
+        for (int j = lane; j < 72; j += 32) buf[j] = ((const unsigned char*)words)[i * 72 + j];
+        __syncwarp();
+        unsigned* pl = reinterpret_cast<unsigned*>(scr + 128);
+        warp_imbe_decode(sh, buf, lane, pl);
+        if (lane < 15) ((unsigned*)out_data)[i * 15 + lane] = pl[lane];
+        if (lane == 0) out_nerr[i] = 0;
+    } else if (kind == 12) {
+        unsigned d = 0;
+        const int r = warp_bch_decode(sh.T, scr, ((const unsigned long long*)words)[i], lane, &d);
+        if (lane == 0) {
+            out_nerr[i] = r;
+            ((unsigned*)out_data)[i] = d;
+        }
+    } else {
+        for (int j = lane; j < 98; j += 32) buf[j] = ((const unsigned char*)words)[i * 98 + j];
+        __syncwarp();
+        unsigned char* out = sh.ws[warp].hex;
+        const int r = warp_trellis_half_decode(sh.T, scr, buf, lane, out);
+        __syncwarp();
+        if (lane < 12) ((unsigned char*)out_data)[i * 12 + lane] = r < 0 ? 0 : out[lane];
+        if (lane == 0) out_nerr[i] = r;
+    }
+}
+
 cudaError_t p25cu_launch_fec_selftest(const P25DevTables* tables, int kind, void* words, size_t count, int n, int k,
                                       void* out_data, int32_t* out_nerr, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    if (kind >= 10 && kind <= 13) {
+        const unsigned wb = (unsigned)((count + P25CU_WALK_WARPS - 1) / P25CU_WALK_WARPS);
+        p25_fec_selftest_warp_kernel<<<wb, 32 * P25CU_WALK_WARPS, 0, st>>>(tables, kind, words, count, n, k, out_data, out_nerr);
+        return cudaGetLastError();
+    }
     const unsigned blocks = (unsigned)((count + 127) / 128);
     if (blocks == 0) return cudaSuccess;
 #define P25_ST_CASE(K) case K: p25_fec_selftest_kernel<K><<<blocks, 128, 0, st>>>(tables, words, count, n, k, out_data, out_nerr); break;

@@ -460,13 +460,14 @@ extern "C" int p25cu_device_baseband(p25cu_ctx* ctx, const float** ptr, size_t* 
 // ---------------------------------------------------------------- FEC unit entry point
 extern "C" int p25cu_fec_selftest(p25cu_ctx* ctx, int kind, void* words, size_t count, int n, int k, void* out_data,
                                   int32_t* out_nerr) {
-    if (!ctx || !words || !out_nerr || kind < 0 || kind > 9) return P25CU_ERR_ARG;
-    if (kind == 7 && (n < 1 || n > 36 || k < 1 || k >= n || ((n - k) != 8 && (n - k) != 12 && (n - k) != 16)))
+    if (!ctx || !words || !out_nerr || kind < 0 || kind > 13) return P25CU_ERR_ARG;
+    const int base_kind = kind == 10 ? 7 : kind == 11 ? 9 : kind == 12 ? 0 : kind == 13 ? 8 : kind;
+    if (base_kind == 7 && (n < 1 || n > 36 || k < 1 || k >= n || ((n - k) != 8 && (n - k) != 12 && (n - k) != 16)))
         return fail_arg(ctx, "rs selftest: unsupported (n, k)");
-    if (kind != 7 && !out_data) return P25CU_ERR_ARG;
+    if (base_kind != 7 && !out_data) return P25CU_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
     size_t in_b, out_b;
-    switch (kind) {
+    switch (base_kind) {
         case 0: in_b = 8; out_b = 4; break;
         case 7: in_b = (size_t)n; out_b = 0; break;
         case 8: in_b = 98; out_b = 12; break;
@@ -485,7 +486,7 @@ extern "C" int p25cu_fec_selftest(p25cu_ctx* ctx, int kind, void* words, size_t 
     CKF(cudaMemcpyAsync(d_in, words, count * in_b, cudaMemcpyHostToDevice, ctx->stream));
     CKF(p25cu_launch_fec_selftest(ctx->d_tables, kind, d_in, count, n, k, d_out, d_nerr, ctx->stream));
     ctx->launches++;
-    if (kind == 7) CKF(cudaMemcpyAsync(words, d_in, count * in_b, cudaMemcpyDeviceToHost, ctx->stream));
+    if (base_kind == 7) CKF(cudaMemcpyAsync(words, d_in, count * in_b, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_b) CKF(cudaMemcpyAsync(out_data, d_out, count * out_b, cudaMemcpyDeviceToHost, ctx->stream));
     CKF(cudaMemcpyAsync(out_nerr, d_nerr, count * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CKF(cudaStreamSynchronize(ctx->stream));

@@ -139,6 +139,7 @@ class Context:
 
     def fec_selftest(self, kind: int, words: np.ndarray, n: int = 0, k: int = 0):
         words = np.ascontiguousarray(words)
+        warp_kind, kind = kind, {10: 7, 11: 9, 12: 0, 13: 8}.get(kind, kind)   # 10..13: warp-cooperative forms
         if kind == 0:
             count, out = words.size, np.zeros(words.size, dtype=np.uint32)
         elif kind == 7:
@@ -152,7 +153,7 @@ class Context:
         else:
             count, out = words.size, np.zeros(words.size, dtype=np.uint32)
         nerr = np.zeros(count, dtype=np.int32)
-        self._ck(self._L.p25cu_fec_selftest(self._h, kind, words.ctypes.data_as(C.c_void_p), count, n, k,
+        self._ck(self._L.p25cu_fec_selftest(self._h, warp_kind, words.ctypes.data_as(C.c_void_p), count, n, k,
                                             out.ctypes.data_as(C.c_void_p) if out is not None else None,
                                             nerr.ctypes.data_as(C.c_void_p)))
         return (words if kind == 7 else out), nerr

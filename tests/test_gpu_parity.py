@@ -44,13 +44,14 @@ def test_fec_decoders_bit_exact(p25, oracle):
         for p in rng.choice(63, int(rng.integers(0, 16)), replace=False):
             w ^= 1 << int(p)
         words[i] = w if i % 5 else int(rng.integers(0, 1 << 63))
-    data, nerr = ctx.fec_selftest(0, words)
-    for i in range(0, n, 7):
-        od, on = C.c_uint16(), C.c_int()
-        ok = O.p25o_bch_decode(int(words[i]), C.byref(od), C.byref(on))
-        assert (nerr[i] >= 0) == bool(ok)
-        if ok:
-            assert nerr[i] == on.value and data[i] == od.value
+    for gk in (0, 12):    # per-thread decoder, then the warp-cooperative form the walker uses
+        data, nerr = ctx.fec_selftest(gk, words)
+        for i in range(0, n, 7):
+            od, on = C.c_uint16(), C.c_int()
+            ok = O.p25o_bch_decode(int(words[i]), C.byref(od), C.byref(on))
+            assert (nerr[i] >= 0) == bool(ok), (gk, i)
+            if ok:
+                assert nerr[i] == on.value and data[i] == od.value, (gk, i)
     # short codes: random words (every syndrome class is exercised)
     for kind, name, bits in ((1, "golay23", 23), (2, "golay24", 24), (3, "golay18", 18), (4, "hamming15", 15),
                              (5, "hamming10", 10), (6, "cyclic16", 16)):
@@ -70,11 +71,11 @@ def test_fec_decoders_bit_exact(p25, oracle):
                 cw[int(p)] ^= int(rng.integers(1, 64))
             blocks[i] = cw if i % 4 else rng.integers(0, 64, nn)
         ref = blocks.copy()
-        fixed, nerr = ctx.fec_selftest(7, blocks.copy(), nn, kk)
-        fixed = fixed.reshape(-1, nn)
+        got = [ctx.fec_selftest(gk, blocks.copy(), nn, kk) for gk in (7, 10)]
         for i in range(len(ref)):
             r = O.p25o_rs_decode(ref[i].ctypes.data_as(C.c_void_p), nn, kk)
-            assert r == nerr[i] and (ref[i] == fixed[i]).all()
+            for fixed, nerr in got:
+                assert r == nerr[i] and (ref[i] == fixed.reshape(-1, nn)[i]).all(), (nn, kk, i)
     # trellis + IMBE
     blocks = np.zeros((4000, 98), dtype=np.uint8)
     for i in range(len(blocks)):
@@ -82,22 +83,24 @@ def test_fec_decoders_bit_exact(p25, oracle):
         for p in rng.choice(196, int(rng.integers(0, 20)), replace=False):
             d[int(p) // 2] ^= 2 >> (int(p) & 1)
         blocks[i] = d if i % 5 else rng.integers(0, 4, 98)
-    out, nerr = ctx.fec_selftest(8, blocks)
+    got = [ctx.fec_selftest(gk, blocks) for gk in (8, 13)]
     for i in range(len(blocks)):
         o = np.zeros(12, np.uint8)
         r = O.p25o_trellis_half_decode(blocks[i].ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
-        assert r == nerr[i] and (r < 0 or (o == out[i]).all())
+        for out, nerr in got:
+            assert r == nerr[i] and (r < 0 or (o == out[i]).all()), i
     blocks = np.zeros((4000, 72), dtype=np.uint8)
     for i in range(len(blocks)):
         d = S.imbe_encode([int(rng.integers(0, 1 << b)) for b in S.IMBE_U_BITS]).copy()
         for p in rng.choice(144, int(rng.integers(0, 14)), replace=False):
             d[int(p) // 2] ^= 2 >> (int(p) & 1)
         blocks[i] = d
-    out, _ = ctx.fec_selftest(9, blocks)
+    got = [ctx.fec_selftest(gk, blocks)[0] for gk in (9, 11)]
     for i in range(len(blocks)):
         c, e = np.zeros(8, np.uint32), np.zeros(7, np.uint32)
         O.p25o_imbe_decode(blocks[i].ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p))
-        assert (out[i, :8] == c).all() and (out[i, 8:] == e).all()
+        for out in got:
+            assert (out[i, :8] == c).all() and (out[i, 8:] == e).all(), i
     ctx.close()
 
 
