@@ -28,10 +28,16 @@ __constant__ float c_sync_fp[P25_FP_LEN];
 #define SEARCH_N 128                          // candidate positions per search step (4 per lane)
 #define WIN_LEN (P25_FP_LEN - 1 + SEARCH_N)  // samples needed to correlate them
 
+struct PendingEvent {
+    unsigned kind, len, valid, pad;
+    unsigned long long idx;
+};
+
 struct WalkShared {
     P25DevTables T;
     WalkState ws[P25CU_WALK_WARPS];
     float win[P25CU_WALK_WARPS][WIN_LEN + 2];
+    PendingEvent pend[P25CU_WALK_WARPS];
     alignas(16) unsigned char scr[P25CU_WALK_WARPS][192];   // decoder work area (syndromes, locator, IMBE results)
     unsigned short pn_a[116], pn_c[116];        // IMBE PN generator n steps ahead: p_n = pn_a[n] * p_0 + pn_c[n] (mod 2^16)
     unsigned char imbe_src[8 * 24];             // inverse of the IMBE interleave schedule: [code word][bit] -> frame bit
@@ -53,6 +59,8 @@ struct WarpCtx {
     const P25DevTables* T;
     WalkState* ws;
     unsigned stream;
+    PendingEvent* pend;       // event decided by lane 0 at this decision point (at most one), written out by the warp
+    unsigned char* payload;   // its payload bytes (shared memory, 60 bytes)
 };
 
 // ---------------------------------------------------------------- lane-0 helpers
@@ -67,26 +75,47 @@ __device__ __forceinline__ void stat_bad(const WarpCtx& c, int fam) {
     s[1] += 1;
 }
 
-__device__ __noinline__ void emit(const WarpCtx& c, unsigned kind, unsigned long long idx, const void* payload, unsigned len) {
+// lane 0: queue the (single) event of this decision point; flush_event() writes it out with the whole warp
+__device__ __forceinline__ void emit(const WarpCtx& c, unsigned kind, unsigned long long idx, const void* payload, unsigned len) {
     WalkState& ws = *c.ws;
     if (ws.n_events >= c.p->ev_cap) {
         ws.overflow = 1;
         return;
     }
-    union {
-        p25cu_event e;
-        uint4 q[5];
-    } u;
-    for (int i = 0; i < 5; i++) u.q[i] = make_uint4(0, 0, 0, 0);
-    u.e.stream = c.stream;
-    u.e.kind = kind;
-    u.e.sample = idx;
-    u.e.len = len;
     const unsigned char* src = (const unsigned char*)payload;
-    for (unsigned i = 0; i < len; i++) u.e.payload[i] = src[i];
-    uint4* dst = (uint4*)(c.p->slots + (size_t)c.stream * c.p->ev_cap + ws.n_events);
-    for (int i = 0; i < 5; i++) dst[i] = u.q[i];
-    ws.n_events++;
+    if (src != c.payload)
+        for (unsigned i = 0; i < len; i++) c.payload[i] = src[i];
+    c.pend->kind = kind;
+    c.pend->len = len;
+    c.pend->idx = idx;
+    c.pend->valid = 1;
+}
+
+// whole warp: one 80-byte event record = 20 words, one per lane (payload bytes beyond len are zero)
+__device__ __forceinline__ void flush_event(const WarpCtx& c, int lane) {
+    if (!c.pend->valid) return;
+    WalkState& ws = *c.ws;
+    const unsigned len = c.pend->len;
+    unsigned w = 0;
+    if (lane == 0) w = c.stream;
+    else if (lane == 1) w = c.pend->kind;
+    else if (lane == 2) w = (unsigned)c.pend->idx;
+    else if (lane == 3) w = (unsigned)(c.pend->idx >> 32);
+    else if (lane == 4) w = len;
+    else if (lane < 20) {
+        const unsigned b0 = 4 * (lane - 5);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (b0 + i < len) w |= (unsigned)c.payload[b0 + i] << (8 * i);
+    }
+    unsigned* dst = (unsigned*)(c.p->slots + (size_t)c.stream * c.p->ev_cap + ws.n_events);
+    if (lane < 20) dst[lane] = w;
+    __syncwarp();
+    if (lane == 0) {
+        ws.n_events++;
+        c.pend->valid = 0;
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ void enter_sync(WalkState& ws, unsigned long long pos) {
@@ -436,6 +465,20 @@ __device__ __forceinline__ void tsbk_apply(const WarpCtx& c, unsigned long long 
     emit(c, P25CU_EV_TSBK, idx, out, 12);
 }
 
+// hexbits (6 bits each, MSB first) -> bytes, one output byte per lane (same packing as p25_pack_hexbits)
+__device__ __forceinline__ void warp_pack_hexbits(const unsigned char* hex, int nhex, unsigned char* out, int lane) {
+    if (lane < nhex * 6 / 8) {
+        unsigned v = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int b = 8 * lane + k;
+            v = (v << 1) | ((hex[b / 6] >> (5 - b % 6)) & 1u);
+        }
+        out[lane] = (unsigned char)v;
+    }
+    __syncwarp();
+}
+
 // lane 0 adds a batch of code-word outcomes to a stats family (n words, `bad` of them uncorrectable, `fixed` bits)
 __device__ __forceinline__ void stat_batch(const WarpCtx& c, int fam, unsigned n, unsigned bad, unsigned fixed) {
     unsigned* s = c.p->stats + ((size_t)c.stream * P25CU_ST_FAMILIES + fam) * 3;
@@ -481,6 +524,8 @@ __device__ __noinline__ void complete_payload(const WarpCtx& c, const WalkShared
         nfix = __reduce_add_sync(FULL, nfix);
         __syncwarp();
         const int n = warp_rs_decode(T, scr, ws.hex, hdu ? 36 : 24, hdu ? 20 : 12, lane);
+        __syncwarp();
+        if (n >= 0) warp_pack_hexbits(ws.hex, hdu ? 20 : 12, c.payload, lane);
         if (lane == 0) {
             stat_batch(c, hdu ? P25CU_ST_GOLAY_SHORT : P25CU_ST_GOLAY_EXT, (unsigned)nw, nbad, nfix);
             const int fam = hdu ? P25CU_ST_RS_LONG : P25CU_ST_RS_SHORT;
@@ -489,10 +534,8 @@ __device__ __noinline__ void complete_payload(const WarpCtx& c, const WalkShared
                 fail(c, P25CU_E_RS, idx);
             } else {
                 stat_ok(c, fam, (unsigned)n);
-                unsigned char out[15];
-                p25_pack_hexbits(ws.hex, hdu ? 20 : 12, out);
                 ws.state = WS_FLUSH;
-                emit(c, hdu ? P25CU_EV_VOICE_HEADER : P25CU_EV_VOICE_TERM, idx, out, hdu ? 15 : 9);
+                emit(c, hdu ? P25CU_EV_VOICE_HEADER : P25CU_EV_VOICE_TERM, idx, c.payload, hdu ? 15 : 9);
             }
         }
         return;
@@ -527,7 +570,11 @@ __device__ __noinline__ void complete_payload(const WarpCtx& c, const WalkShared
         __syncwarp();
         const bool lc = duid == 0x5;
         int n = 0;
-        if (chunks + 1 == 6) n = warp_rs_decode(T, scr, ws.hex, 24, lc ? 12 : 16, lane);
+        if (chunks + 1 == 6) {
+            n = warp_rs_decode(T, scr, ws.hex, 24, lc ? 12 : 16, lane);
+            __syncwarp();
+            if (n >= 0) warp_pack_hexbits(ws.hex, lc ? 12 : 16, c.payload, lane);
+        }
         if (lane == 0) {
             ws.part = part + 1;
             ws.chunks = chunks + 1;
@@ -539,9 +586,7 @@ __device__ __noinline__ void complete_payload(const WarpCtx& c, const WalkShared
                     fail(c, P25CU_E_RS, idx);
                 } else {
                     stat_ok(c, fam, (unsigned)n);
-                    unsigned char out[12];
-                    p25_pack_hexbits(ws.hex, lc ? 12 : 16, out);
-                    emit(c, lc ? P25CU_EV_LINK_CONTROL : P25CU_EV_CRYPTO_CONTROL, idx, out, lc ? 9 : 12);
+                    emit(c, lc ? P25CU_EV_LINK_CONTROL : P25CU_EV_CRYPTO_CONTROL, idx, c.payload, lc ? 9 : 12);
                 }
             }
         }
@@ -597,7 +642,9 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
     __syncthreads();
     if (!active) return;
 
-    WarpCtx c{&p, &sh.T, &ws, stream};
+    WarpCtx c{&p, &sh.T, &ws, stream, &sh.pend[warp], sh.scr[warp] + 128};
+    if (lane == 0) sh.pend[warp].valid = 0;
+    __syncwarp();
     float* win = sh.win[warp];
     const unsigned long long p0 = p.p0, end = p.p0 + p.n;
     const float* row = p.bb + (size_t)stream * p.row_stride;  // row[i] <-> absolute sample p0 - 256 + i
@@ -782,6 +829,7 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
                 complete_payload(c, sh, sh.scr[warp], idx, lane);
             }
             __syncwarp();
+            flush_event(c, lane);
         }
     }
 

@@ -296,3 +296,65 @@ def test_full_size_properties(p25):
         assert key == per[(s % 8, s // 8 % 4)]
         assert len(key) >= 12
     ctx.close()
+
+
+# ------------------------------------------------------------------ BASELINE.json configs[3]: voice at low SNR with CFO
+def _voice_streams(n_streams: int, pairs: int):
+    """HDU, alternating LDU1/LDU2, TDULC; SNR swept over {6, 8, 10, 12, 15} dB."""
+    return [tx.traffic_channel(4000 + s, pairs) for s in range(n_streams)], [6, 8, 10, 12, 15]
+
+
+def test_cfg4_voice_low_snr_decode_bit_exact(p25, oracle):
+    """256 traffic-channel streams at 6..15 dB: every Golay / Hamming / RS / cyclic path runs with real errors
+    and failures; events, payloads (IMBE u0..u7 + error counts, LC, ES, LSD, HDU) and all stats are bit-exact."""
+    S_ = 256
+    streams, snrs = _voice_streams(S_, 2)
+    rows = [tx.baseband_48k(st.dibits, snr_db=snrs[s % 5], seed=s, dc=0.01 * ((s % 7) - 3), timing_offset=0.37 * (s % 10))[0]
+            for s, st in enumerate(streams)]
+    n = min(len(r) for r in rows)
+    bb = np.stack([r[:n] for r in rows])
+    ref, ref_stats = oracle_events(oracle, bb)
+    ctx = p25.Context(S_, max_chunk_samples=1024, max_baseband=8192)
+    rx = p25.MessageReceiver(ctx)
+    ev = np.concatenate([rx.feed(bb[:, i:i + 8192]) for i in range(0, n, 8192)])   # the replay block size (src/replay.rs:27)
+    ev = ev[np.lexsort((ev["sample"], ev["stream"]))]
+    assert events_key(ev) == events_key(ref)
+    got_stats = np.stack([ctx.stats(s) for s in range(S_)])
+    assert (got_stats == np.stack(ref_stats)).all()
+    kinds = np.bincount(ev["kind"], minlength=9)
+    assert kinds[p25.EV_VOICE_FRAME] > 30 * S_ and kinds[p25.EV_ERROR] > 0 and kinds[p25.EV_LINK_CONTROL] > 0
+    fam = got_stats.sum(axis=0)                  # every voice-path code family saw words and corrected bits
+    for f in ("golayStd", "golayExt", "golayShort", "hammingStd", "hammingShort", "rsShort", "rsMed", "rsLong", "cyclic", "bch"):
+        i = p25.STATS_FAMILIES.index(f)
+        assert fam[i, 0] > 0 and fam[i, 3] > 0, f
+    ctx.close()
+
+
+def test_cfg4_voice_iq_cfo_end_to_end(p25, oracle):
+    """The same signals as 240 kS/s u8 IQ with +-300 Hz carrier offset through the whole path (ddc_fm /5 fast kernel +
+    walker) against the oracle chain.  The front ends agree to ~1e-6, so slicer decisions can differ only on samples
+    that sit within that distance of a threshold: the event lists must agree except for a stated, tiny fraction."""
+    S_ = 40
+    streams, snrs = _voice_streams(S_, 1)
+    rng = np.random.default_rng(44)
+    rows = [tx.iq_to_u8(tx.modulate_iq(st.dibits, 240_000, snr_db=snrs[s % 5] + 6.0, cfo_hz=float(rng.uniform(-300, 300)), seed=s))
+            for s, st in enumerate(streams)]
+    n = min(len(r) for r in rows) // 2 // 16384 * 16384
+    data = np.stack([r[: 2 * n] for r in rows])
+    ctx = p25.Context(S_, fmt=p25.FMT_U8_IQ, decimation=5, max_chunk_samples=16384)
+    got = []
+    for i in range(0, n, 16384):                                        # the reference's SDR chunk (src/consts.rs:6)
+        ctx.process(np.ascontiguousarray(data[:, 2 * i: 2 * (i + 16384)]), 16384)
+        got.append(ctx.poll())
+    got = np.concatenate(got)
+    got = got[np.lexsort((got["sample"], got["stream"]))]
+    ref = []
+    for s in range(S_):
+        bb = oracle.DemodChain(oracle.FMT_U8, False).feed(data[s])
+        ref.append(oracle.MessageReceiver(stream=s).feed(bb))
+    ref = np.concatenate(ref)
+    a, b = set(events_key(got)), set(events_key(ref))
+    diff = len(a ^ b)
+    assert len(ref) > 25 * S_
+    assert diff <= max(2, len(ref) // 500), f"{diff} of {len(ref)} events differ"
+    ctx.close()
