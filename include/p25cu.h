@@ -44,8 +44,14 @@ typedef enum {
 typedef enum { P25CU_FMT_U8_IQ = 0, P25CU_FMT_CF32_IQ = 1 } p25cu_format;
 
 /* Decimation from the input rate to the 48 kHz baseband rate (reference src/consts.rs:11-13).
- * 5  : 240 kS/s input, the reference's own chain               (reference src/demod.rs:50)
- * 50 : 2.4 MS/s input, a /10 front stage ahead of the same chain (BASELINE.json configs[0]) */
+ * 5   : 240 kS/s input, the reference's own chain               (reference src/demod.rs:50)
+ * 50  : 2.4 MS/s input, a /10 front stage ahead of the same chain (BASELINE.json configs[0])
+ * 400 : wideband channelizer (BASELINE.json configs[2]; declared extension, the reference has one tuner and one
+ *       channel, src/sdr.rs:61-68): every input row is a 19.2 MS/s cf32 capture that a polyphase filter bank splits
+ *       into 1,536 channels 12.5 kHz apart, each delivered at 48 kS/s and run through the reference's 48 kHz stages
+ *       (src/demod.rs:93-114).  n_streams must be a multiple of 1536: stream = capture * 1536 + channel, channel k
+ *       is centred k * 12.5 kHz above the capture centre (k >= 768: (k - 1536) * 12.5 kHz).  format must be CF32_IQ;
+ *       p25cu_demod takes [n_streams / 1536][n_in] samples. */
 typedef struct {
     int32_t device;             /* CUDA device ordinal */
     uint32_t n_streams;         /* independent streams held by this context */
@@ -153,6 +159,10 @@ int p25cu_set_overlap(p25cu_ctx* ctx, int on);
 uint64_t p25cu_launch_count(const p25cu_ctx* ctx);
 /* Device pointer/row stride (in floats) of the baseband produced by the last p25cu_demod. */
 int p25cu_device_baseband(p25cu_ctx* ctx, const float** ptr, size_t* row_stride, size_t* n_out);
+
+/* Channelizer mode only: copy the channel spectra of the last p25cu_demod, [captures][*n_rows][1536] complex float32
+ * (48 kS/s per channel, before the channel-select filter), to `out` (nullable: only report *n_rows). */
+int p25cu_channelizer_output(p25cu_ctx* ctx, float* out, size_t* n_rows);
 
 /* ---- FEC unit entry points: run the device decoders on caller-provided code words (one word per
  * GPU thread), used by the parity tests to compare each decoder with the oracle in bulk.

@@ -325,8 +325,8 @@ size_t DemodChain::feed(const void* iq, size_t n, float* out, float* power_dbm) 
         else
             s = cf[i];
         if (use_front_ && !front_.feed(s, &s)) continue;
-        cf32 d;
-        if (!decim_.feed(s, &d)) continue;        // src/demod.rs:87
+        cf32 d = s;
+        if (!skip_decim_ && !decim_.feed(s, &d)) continue;        // src/demod.rs:87
         cf32 c = chan_.feed(d);                   // src/demod.rs:93
         pacc += c.re * c.re + c.im * c.im;        // src/demod.rs:125-127
         float f = fm_.feed(c);                    // src/demod.rs:109-111
@@ -637,7 +637,7 @@ extern "C" {
 
 void p25o_set_always_correlate(int on) { g_always_correlate = on != 0; }
 
-void* p25o_demod_new(int fmt, int front) { return new DemodChain(fmt, front != 0); }
+void* p25o_demod_new(int fmt, int mode) { return new DemodChain(fmt, mode); }
 void p25o_demod_free(void* h) { delete (DemodChain*)h; }
 size_t p25o_demod_feed(void* h, const void* iq, size_t n, float* out, float* power_dbm) {
     return ((DemodChain*)h)->feed(iq, n, out, power_dbm);

@@ -196,16 +196,19 @@ enum IqFormat { FMT_U8 = 0, FMT_CF32 = 1 };
 // DemodTask::run loop body (src/demod.rs:70-117) for one stream.
 class DemodChain {
 public:
-    // front: prepend the /10 stage for 2.4 MS/s input (declared extension)
-    DemodChain(int fmt, bool front)
-        : fmt_(fmt), use_front_(front), front_(P25_TAPS_FRONT_H, P25_DECIM_FRONT), decim_(P25_TAPS_DECIM_H, P25_DECIM_NATIVE), chan_(P25_TAPS_CHAN_H) {}
+    // mode 0: the reference chain (/5); mode 1: prepend the /10 stage for 2.4 MS/s input (declared extension,
+    // SURVEY F4); mode 2: input is already at 48 kS/s (one output channel of the wideband channelizer): only the
+    // reference's 48 kHz stages run (src/demod.rs:93-114)
+    DemodChain(int fmt, int mode)
+        : fmt_(fmt), use_front_(mode == 1), skip_decim_(mode == 2), front_(P25_TAPS_FRONT_H, P25_DECIM_FRONT),
+          decim_(P25_TAPS_DECIM_H, P25_DECIM_NATIVE), chan_(P25_TAPS_CHAN_H) {}
     // feeds n IQ samples, writes baseband samples, returns their count.
     // power_dbm (nullable) receives power_dbm() of this call's channel-filtered samples.
     size_t feed(const void* iq, size_t n, float* out, float* power_dbm);
 
 private:
     int fmt_;
-    bool use_front_;
+    bool use_front_, skip_decim_;
     Decimator<P25_TAPS_FRONT> front_;
     Decimator<P25_TAPS_DECIM> decim_;
     FirFilter<P25_TAPS_CHAN> chan_;

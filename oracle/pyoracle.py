@@ -74,10 +74,12 @@ def _ptr(a: np.ndarray):
 class DemodChain:
     """One stream's DemodTask::run body (reference src/demod.rs:70-117)."""
 
-    def __init__(self, fmt: int, front: bool, native: bool = False):
+    def __init__(self, fmt: int, front, native: bool = False):
+        """front: False / 0 = reference chain (/5), True / 1 = /10 front stage first (2.4 MS/s input),
+        2 = input already at 48 kS/s (a channelizer output): 48 kHz stages only."""
         self._L = lib(native)
         self._h = self._L.p25o_demod_new(fmt, int(front))
-        self.fmt, self.front = fmt, front
+        self.fmt, self.front = fmt, int(front)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -91,7 +93,7 @@ class DemodChain:
         else:
             iq = np.ascontiguousarray(iq, dtype=np.complex64)
             n = iq.size
-        out = np.empty(n // (50 if self.front else 5) + 2, dtype=np.float32)
+        out = np.empty(n // {0: 5, 1: 50, 2: 1}[self.front] + 2, dtype=np.float32)
         p = C.c_float(0)
         m = self._L.p25o_demod_feed(self._h, _ptr(iq), n, _ptr(out), C.byref(p) if want_power else None)
         return (out[:m], p.value) if want_power else out[:m]

@@ -14,6 +14,16 @@
 
 unsigned p25cu_ddc_block_out(int decimation);
 cudaError_t p25cu_walk_upload_consts();
+// wideband channelizer (pfb.cu)
+unsigned p25cu_pfb_tail_len();
+unsigned p25cu_pfb_channels();
+unsigned p25cu_pfb_decimation();
+unsigned p25cu_pfb_hist_rows();
+cudaError_t p25cu_pfb_upload(float** d_taps, float2** d_twiddle);
+cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out, const float* taps, const float2* twiddle, float2* y,
+                             unsigned y_rows, float* bb, size_t row_stride, float* power_sum, unsigned long long a0,
+                             unsigned long long m0, unsigned n, unsigned n_out, unsigned n_captures, cudaStream_t st,
+                             unsigned* launches);
 
 struct p25cu_ctx {
     p25cu_config cfg;
@@ -48,6 +58,13 @@ struct p25cu_ctx {
     bool dev_bb_fresh;
     unsigned long long launches;
     int n_sm;
+    // wideband channelizer mode (decimation 400): input rows are captures, streams are their channels
+    unsigned n_captures;       // 0 = one stream per input row
+    float* d_pfb_taps;
+    float2* d_twiddle;
+    float2* d_y;               // [captures][y_rows][1536] channel spectra, time-major
+    float2* d_ytmp;            // [captures][hist][1536] staging for the carried history rows
+    unsigned y_rows;
 };
 
 static char g_create_err[512] = "";
@@ -85,6 +102,10 @@ extern "C" void p25cu_destroy(p25cu_ctx* ctx) {
     cudaFree(ctx->d_offsets);
     cudaFree(ctx->d_stats);
     cudaFree(ctx->d_tables);
+    cudaFree(ctx->d_pfb_taps);
+    cudaFree(ctx->d_twiddle);
+    cudaFree(ctx->d_y);
+    cudaFree(ctx->d_ytmp);
     cudaFreeHost(ctx->h_events);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_bb_ready[i]) cudaEventDestroy(ctx->ev_bb_ready[i]);
@@ -121,16 +142,27 @@ static int create_impl(p25cu_ctx* ctx) {
     }
     ctx->overlap = 1;
     const size_t S = cfg.n_streams;
-    ctx->ht = p25cu_ddc_tail_len(cfg.decimation);
+    const bool wide = cfg.decimation == (int)p25cu_pfb_decimation();
+    ctx->n_captures = wide ? cfg.n_streams / p25cu_pfb_channels() : 0;
+    ctx->ht = wide ? p25cu_pfb_tail_len() : p25cu_ddc_tail_len(cfg.decimation);
     ctx->max_out = cfg.max_chunk_samples / cfg.decimation + 1;
     if (cfg.max_baseband > ctx->max_out) ctx->max_out = cfg.max_baseband;
     ctx->row_stride = (P25CU_BB_HIST + ctx->max_out + 3) & ~(size_t)3;
     ctx->ev_cap = cfg.event_slots ? cfg.event_slots : (unsigned)(ctx->max_out / 200 + 16);
 
-    CK(cudaMalloc(&ctx->d_tail[0], S * ctx->ht * sizeof(float2)));
-    CK(cudaMalloc(&ctx->d_tail[1], S * ctx->ht * sizeof(float2)));
-    CK(cudaMemsetAsync(ctx->d_tail[0], 0, S * ctx->ht * sizeof(float2), ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_tail[1], 0, S * ctx->ht * sizeof(float2), ctx->stream));
+    const size_t tail_rows = wide ? ctx->n_captures : S;
+    CK(cudaMalloc(&ctx->d_tail[0], tail_rows * ctx->ht * sizeof(float2)));
+    CK(cudaMalloc(&ctx->d_tail[1], tail_rows * ctx->ht * sizeof(float2)));
+    CK(cudaMemsetAsync(ctx->d_tail[0], 0, tail_rows * ctx->ht * sizeof(float2), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_tail[1], 0, tail_rows * ctx->ht * sizeof(float2), ctx->stream));
+    if (wide) {
+        const size_t ch = p25cu_pfb_channels(), hist = p25cu_pfb_hist_rows();
+        ctx->y_rows = (unsigned)(hist + ctx->max_out);
+        CK(cudaMalloc(&ctx->d_y, (size_t)ctx->n_captures * ctx->y_rows * ch * sizeof(float2)));
+        CK(cudaMemsetAsync(ctx->d_y, 0, (size_t)ctx->n_captures * ctx->y_rows * ch * sizeof(float2), ctx->stream));
+        CK(cudaMalloc(&ctx->d_ytmp, (size_t)ctx->n_captures * hist * ch * sizeof(float2)));
+        CK(p25cu_pfb_upload(&ctx->d_pfb_taps, &ctx->d_twiddle));
+    }
     for (int i = 0; i < 2; i++) {
         CK(cudaMalloc(&ctx->d_bb[i], S * ctx->row_stride * sizeof(float)));
         CK(cudaMemsetAsync(ctx->d_bb[i], 0, S * ctx->row_stride * sizeof(float), ctx->stream));
@@ -173,8 +205,10 @@ extern "C" int p25cu_create(const p25cu_config* cfg, p25cu_ctx** out) {
     }
     *out = nullptr;
     if (cfg->abi_version != P25CU_ABI_VERSION || cfg->n_streams == 0 || cfg->max_chunk_samples == 0 ||
-        (cfg->decimation != 5 && cfg->decimation != 50) ||
-        (cfg->format != P25CU_FMT_U8_IQ && cfg->format != P25CU_FMT_CF32_IQ)) {
+        (cfg->decimation != 5 && cfg->decimation != 50 && cfg->decimation != (int)p25cu_pfb_decimation()) ||
+        (cfg->format != P25CU_FMT_U8_IQ && cfg->format != P25CU_FMT_CF32_IQ) ||
+        (cfg->decimation == (int)p25cu_pfb_decimation() &&
+         (cfg->format != P25CU_FMT_CF32_IQ || cfg->n_streams % p25cu_pfb_channels() != 0))) {
         snprintf(g_create_err, sizeof g_create_err,
                  "bad config (abi_version %u, n_streams %u, format %d, decimation %d, max_chunk_samples %llu)",
                  cfg->abi_version, cfg->n_streams, cfg->format, cfg->decimation,
@@ -204,9 +238,10 @@ extern "C" int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_d
     CK(cudaSetDevice(ctx->cfg.device));
     const size_t S = ctx->cfg.n_streams;
     const size_t bps = ctx->cfg.format == P25CU_FMT_U8_IQ ? 2 : 8;
+    const size_t in_rows = ctx->n_captures ? ctx->n_captures : S;
     const void* d_in = iq;
     if (!iq_on_device && n) {
-        const size_t bytes = S * n * bps;
+        const size_t bytes = in_rows * n * bps;
         if (bytes > ctx->d_iq_bytes) {
             CK(cudaStreamSynchronize(ctx->stream));
             cudaFree(ctx->d_iq);
@@ -249,7 +284,22 @@ extern "C" int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_d
         p.n_seg = p.n_out ? (p.n_out + p.seg_out - 1) / p.seg_out : 1;
     }
     if (power_dbm) CK(cudaMemsetAsync(ctx->d_power, 0, S * sizeof(float), ctx->stream));
-    if (n) {
+    if (n && ctx->n_captures) {
+        // wideband capture -> 1,536 channels per capture (pfb.cu): spectra, per-channel baseband, carried state
+        const size_t ch = p25cu_pfb_channels(), hist = p25cu_pfb_hist_rows();
+        unsigned nl = 0;
+        CK(p25cu_launch_pfb(d_in, p.tail_in, p.tail_out, ctx->d_pfb_taps, ctx->d_twiddle, ctx->d_y, ctx->y_rows, p.bb, p.row_stride,
+                            p.power_sum, p.a0, p.m0, p.n, p.n_out, ctx->n_captures, ctx->stream, &nl));
+        ctx->launches += nl;
+        if (p.n_out) {   // the last `hist` rows of (history ++ this chunk) become the next chunk's history
+            const size_t row = ch * sizeof(float2);
+            CK(cudaMemcpy2DAsync(ctx->d_ytmp, hist * row, ctx->d_y + (size_t)p.n_out * ch, (size_t)ctx->y_rows * row, hist * row,
+                                 ctx->n_captures, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpy2DAsync(ctx->d_y, (size_t)ctx->y_rows * row, ctx->d_ytmp, hist * row, hist * row, ctx->n_captures,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        ctx->tail_cur ^= 1;
+    } else if (n) {
         CK(p25cu_launch_ddc(p, ctx->cfg.format, ctx->cfg.decimation, ctx->stream));
         ctx->launches++;
         ctx->tail_cur ^= 1;
@@ -454,6 +504,24 @@ extern "C" int p25cu_device_baseband(p25cu_ctx* ctx, const float** ptr, size_t* 
     *ptr = ctx->d_bb[ctx->bb_last] + P25CU_BB_HIST;
     if (row_stride) *row_stride = ctx->row_stride;
     if (n_out) *n_out = ctx->last_n_out;
+    return P25CU_OK;
+}
+
+extern "C" int p25cu_channelizer_output(p25cu_ctx* ctx, float* out, size_t* n_rows) {
+    if (!ctx || !n_rows) return P25CU_ERR_ARG;
+    if (!ctx->n_captures) {
+        snprintf(ctx->err, sizeof ctx->err, "p25cu_channelizer_output: context is not in channelizer mode (decimation 400)");
+        return P25CU_ERR_STATE;
+    }
+    CK(cudaSetDevice(ctx->cfg.device));
+    *n_rows = ctx->last_n_out;
+    if (out && ctx->last_n_out) {
+        // the carried history (rows 0..63) was refreshed after the chunk, so this chunk's rows start at row `hist` unchanged
+        const size_t ch = p25cu_pfb_channels(), row = ch * sizeof(float2);
+        CK(cudaMemcpy2DAsync(out, ctx->last_n_out * row, ctx->d_y + (size_t)p25cu_pfb_hist_rows() * ch, (size_t)ctx->y_rows * row,
+                             ctx->last_n_out * row, ctx->n_captures, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     return P25CU_OK;
 }
 

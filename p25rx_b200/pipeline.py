@@ -68,7 +68,8 @@ class Context:
     # ---- Surface 1
     def demod(self, iq, n_in_per_stream: int, want_baseband: bool = True, want_power: bool = False):
         """p25cu_demod.  iq: numpy array (host) or torch tensor (host or cuda), [S][n] samples of the
-        context's format.  Returns (baseband [S][n_out] or None, n_out, power_dbm [S] or None)."""
+        context's format ([S / 1536][n] wideband captures when decimation = 400).
+        Returns (baseband [S][n_out] or None, n_out, power_dbm [S] or None)."""
         ptr, on_dev = _as_ptr(iq)
         n = int(n_in_per_stream)
         n_expect = (self._a_abs + n) // self.decimation - self._a_abs // self.decimation
@@ -122,6 +123,15 @@ class Context:
         st = _lib.Stats()
         self._ck(self._L.p25cu_get_stats(self._h, stream, C.byref(st), int(clear)))
         return np.ctypeslib.as_array(st.code).astype(np.uint64).reshape(12, 4).copy()
+
+    def channelizer_output(self) -> np.ndarray:
+        """Channelizer mode (decimation 400): channel spectra of the last demod, [captures][n_out][1536] complex64."""
+        n = C.c_size_t(0)
+        self._ck(self._L.p25cu_channelizer_output(self._h, None, C.byref(n)))
+        out = np.zeros((self.n_streams // 1536, n.value, 1536), dtype=np.complex64)
+        if n.value:
+            self._ck(self._L.p25cu_channelizer_output(self._h, out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return out
 
     def sync(self):
         self._ck(self._L.p25cu_sync(self._h))

@@ -66,6 +66,26 @@ def taps_chan() -> np.ndarray:
     return _kaiser_lowpass(TAPS_CHAN_LEN, 6_250.0, BASEBAND_SAMPLE_RATE, 50.0)
 
 
+# ----------------------------------------------------------------------------
+# Wideband polyphase channelizer [BUILD] (BASELINE.json configs[2]; no reference stage):
+# a 19.2 MS/s cf32 capture is split into 1,536 channels 12.5 kHz apart, each delivered at 48 kS/s
+# (decimation 400, oversampled 3.84x).  Channel k is DEFINED as mix-down by k * 12.5 kHz, the prototype
+# low-pass below, and decimation by 400 with the newest input of output m at index 400 m + 399:
+#     y_k[m] = sum_i h[i] * x[400 m + 399 - i] * exp(-2j pi k (400 m + 399 - i) / 1536)
+# followed by the reference's own 48 kHz stages (channel-select FIR, discriminator, boxcar).
+# ----------------------------------------------------------------------------
+PFB_SAMPLE_RATE = 19_200_000
+PFB_CHANNELS = 1536
+PFB_DECIM = 400
+PFB_TAPS_PER_BRANCH = 4
+PFB_TAPS_LEN = PFB_CHANNELS * PFB_TAPS_PER_BRANCH
+
+
+def taps_pfb() -> np.ndarray:
+    """Prototype low-pass: 16 kHz cutoff, 80 dB Kaiser; pass band flat to +-8 kHz, stop band from 24 kHz."""
+    return _kaiser_lowpass(PFB_TAPS_LEN, 16_000.0, PFB_SAMPLE_RATE, 80.0)
+
+
 def iq_lut() -> np.ndarray:
     """u8 -> f32 mapping of rtlsdr_iq [RECALL, scale unpinned]: (b - 127.5) / 127.5."""
     b = np.arange(256, dtype=np.float32)

@@ -358,3 +358,50 @@ def test_cfg4_voice_iq_cfo_end_to_end(p25, oracle):
     assert len(ref) > 25 * S_
     assert diff <= max(2, len(ref) // 500), f"{diff} of {len(ref)} events differ"
     ctx.close()
+
+
+# ------------------------------------------------------------------ BASELINE.json configs[2]: wideband channelizer
+def test_channelizer_spectra_baseband_and_events(p25, oracle):
+    """19.2 MS/s capture -> 1,536 channels (pfb.cu) against oracle/pfb_oracle.py + the reference's 48 kHz chain:
+    channel spectra and occupied-channel baseband within the FP32 tolerance, decoded events identical, carried state
+    across unequal chunks."""
+    from oracle import pfb_oracle as pfb
+    occupied = {3: 0.05, 100: 0.04, 767: 0.05, 768: 0.03, 1000: 0.05, 1535: 0.04}
+    chans = {k: (tx.control_channel(800 + k, 2, lead_idle=20 + k % 30).dibits, amp, 40.0 * ((k % 5) - 2))
+             for k, amp in occupied.items()}
+    n_out_total = 2 * 3600 + 700
+    n = n_out_total * 400
+    cap = tx.wideband_capture(chans, n, noise_db=-55.0, seed=3)
+    ref_y = pfb.channelize(cap)                                   # [n_out][1536] complex128
+    ctx = p25.Context(1536, fmt=p25.FMT_CF32_IQ, decimation=400, max_chunk_samples=1_600_000, event_slots=64)
+    got_y, got_bb, got_pw, pos = [], [], [], 0
+    for m in (1_000_000, 1_555_556, n - 2_555_556):               # unequal, not multiples of 400
+        bb, n_out, pw = ctx.demod(np.ascontiguousarray(cap[None, pos:pos + m]), m, want_power=True)
+        got_y.append(ctx.channelizer_output()[0])
+        got_bb.append(bb)
+        got_pw.append((pw, n_out))
+        ctx.decode()
+        pos += m
+    ev = ctx.poll()
+    got_y = np.concatenate(got_y)
+    got_bb = np.concatenate(got_bb, axis=1)
+    assert got_y.shape == ref_y.shape == (n_out_total, 1536)
+    scale = np.max(np.abs(ref_y))
+    assert np.max(np.abs(got_y - ref_y)) < 2e-5 * scale, np.max(np.abs(got_y - ref_y)) / scale
+    oracle.lib().p25o_set_always_correlate(0)
+    ref_ev = []
+    for k in range(1536):
+        chain = oracle.DemodChain(oracle.FMT_CF32, 2)
+        rbb = chain.feed(ref_y[:, k].astype(np.complex64))
+        ref_ev.append(oracle.MessageReceiver(stream=k).feed(rbb))
+        if k in occupied:     # carrier present from sample ~0 on: the discriminator is well conditioned
+            assert np.max(np.abs(got_bb[k, 200:] - rbb[200:])) < BB_TOL, k
+    ref_ev = np.concatenate(ref_ev)
+    ev = ev[np.lexsort((ev["sample"], ev["stream"]))]
+    assert events_key(ev) == events_key(ref_ev)
+    # noise-only channels yield false syncs (errors, the odd NID that random bits happen to BCH-decode to) identically
+    # in both; trunking payloads come from the occupied channels only
+    good = ev[ev["kind"] == p25.EV_TSBK]
+    assert sorted(set(int(s) for s in good["stream"])) == sorted(occupied)
+    assert np.count_nonzero(ev["kind"] == p25.EV_TSBK) == 6 * len(occupied)
+    ctx.close()

@@ -1,0 +1,67 @@
+"""CPU checks of the channelizer restatement (oracle/pfb_oracle.py) and of the generated prototype taps."""
+import os
+import re
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "spec"))
+
+import p25_spec as S  # noqa: E402
+from oracle import pfb_oracle as po  # noqa: E402
+from tools import p25tx as tx  # noqa: E402
+
+
+def test_polyphase_form_equals_definition():
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(40000) + 1j * rng.standard_normal(40000)).astype(np.complex64)
+    y = po.channelize(x, 0, 90)
+    for k in (0, 1, 2, 383, 767, 768, 769, 1000, 1535):
+        ms = np.array([0, 1, 14, 15, 16, 40, 89])
+        d = po.channel_direct(x, k, ms)
+        assert np.max(np.abs(y[ms, k] - d)) < 1e-9 * max(1.0, np.max(np.abs(d)))
+
+
+def test_offset_start_matches_whole_stream():
+    rng = np.random.default_rng(6)
+    x = (rng.standard_normal(30000) + 1j * rng.standard_normal(30000)).astype(np.complex64)
+    whole = po.channelize(x, 0, 70)
+    part = po.channelize(x, 33, 20)
+    assert np.allclose(whole[33:53], part, rtol=0, atol=1e-12)
+
+
+def test_prototype_filter_meets_its_spec():
+    h = S.taps_pfb().astype(np.float64)
+    assert len(h) == S.PFB_TAPS_LEN == 6144 and abs(h.sum() - 1.0) < 1e-6
+    H = np.abs(np.fft.rfft(h, 1 << 20))
+    f = np.fft.rfftfreq(1 << 20, 1.0 / S.PFB_SAMPLE_RATE)
+    assert np.max(np.abs(20 * np.log10(H[f <= 6250.0]))) < 0.05            # flat over a 12.5 kHz channel
+    assert np.max(20 * np.log10(H[f >= 24000.0] + 1e-30)) < -75.0          # nothing folds back at 48 kS/s
+
+
+def test_generated_header_holds_these_taps():
+    txt = open(os.path.join(ROOT, "p25rx_b200", "csrc", "p25_pfb_taps.h")).read()
+    body = txt[txt.index("P25_TAPS_PFB_H"):]
+    vals = np.array([float.fromhex(v) for v in re.findall(r"(-?0x[0-9a-fA-F.]+p[-+]?\d+)f", body)], dtype=np.float32)
+    assert len(vals) == S.PFB_TAPS_LEN and (vals == S.taps_pfb()).all()
+    assert f"#define P25_PFB_N {S.PFB_CHANNELS}" in txt and f"#define P25_PFB_M {S.PFB_DECIM}" in txt
+
+
+def test_channel_carries_a_decodable_control_channel():
+    """A transmitter 100 channels up comes out of channel 100 and decodes through the reference's 48 kHz chain."""
+    from oracle import pyoracle as o
+    st = tx.control_channel(7, 2)
+    n = (len(st.dibits) * 10 + 200) * S.PFB_DECIM
+    cap = tx.wideband_capture({100: (st.dibits, 0.05, 30.0)}, n, noise_db=-60.0, seed=1)
+    y = po.channelize(cap)
+    o.lib().p25o_set_always_correlate(0)
+    bb = o.DemodChain(o.FMT_CF32, 2).feed(y[:, 100].astype(np.complex64))
+    ev = o.MessageReceiver().feed(bb)
+    tsbk = [bytes(e["payload"][:12]) for e in ev if e["kind"] == 7]
+    assert len(tsbk) == 6
+    for pl in tsbk:
+        assert S.crc_ccitt_p25(pl[:10]) == (pl[10] << 8 | pl[11])
+    quiet = o.MessageReceiver().feed(o.DemodChain(o.FMT_CF32, 2).feed(y[:, 900].astype(np.complex64)))
+    assert len(quiet) == 0

@@ -326,6 +326,24 @@ def modulate_iq_periodic(dibits: np.ndarray, fs: int, snr_db: float | None = 30.
     return iq.astype(np.complex64)
 
 
+def wideband_capture(channels: dict, n_samples: int, noise_db: float | None = -50.0, seed: int = 0) -> np.ndarray:
+    """A 19.2 MS/s cf32 capture: channels maps a channel number k (0..1535, centre
+    k * 12.5 kHz above the capture centre, k >= 768 below it) to (dibits, amplitude, extra_cfo_hz); white noise of
+    noise_db dBFS total power is added over the whole band."""
+    fs = S.PFB_SAMPLE_RATE
+    out = np.zeros(n_samples, dtype=np.complex128)
+    for k, (dibits, amp, cfo) in channels.items():
+        f = (k if k < S.PFB_CHANNELS // 2 else k - S.PFB_CHANNELS) * 12500.0 + cfo
+        iq = modulate_iq(dibits, fs, snr_db=None, cfo_hz=f, seed=seed + 7 * k, amplitude=amp).astype(np.complex128)
+        m = min(n_samples, len(iq))
+        out[:m] += iq[:m]
+    if noise_db is not None:
+        rng = np.random.default_rng(seed + 99)
+        sigma = np.sqrt(10 ** (noise_db / 10) / 2)
+        out += sigma * (rng.standard_normal(n_samples) + 1j * rng.standard_normal(n_samples))
+    return out.astype(np.complex64)
+
+
 def iq_to_u8(iq: np.ndarray) -> np.ndarray:
     """RTL-SDR style interleaved unsigned bytes (src/sdr.rs:25-33, src/demod.rs:72-84)."""
     v = np.empty(2 * len(iq), dtype=np.float32)
