@@ -26,8 +26,8 @@
 // Device-resident copy of the decode tables (filled from p25_tables.h at context creation;
 // the walker kernel stages it into shared memory).
 struct alignas(16) P25DevTables {
-    float sync_fp[232];
-    uint32_t golay_syn[2048];
+    const uint32_t* golay_syn;   // 2048 entries; stays in global memory (8 KB, L1/L2 resident, voice paths only) so that
+    uint64_t pad_;               // the shared-memory copy of this struct is ~2 KB and walker CTAs co-reside with ddc_fm
     uint16_t cyclic_syn[256];
     uint16_t ham15_syn[16];
     uint16_t ham10_syn[16];
@@ -44,8 +44,8 @@ struct alignas(16) P25DevTables {
 };
 
 static inline void p25_fill_tables(P25DevTables* t) {
-    for (int i = 0; i < 232; i++) t->sync_fp[i] = i < P25_FP_LEN ? P25_SYNC_FP[i] : 0.f;
-    for (int i = 0; i < 2048; i++) t->golay_syn[i] = P25_GOLAY23_SYN[i];
+    t->golay_syn = P25_GOLAY23_SYN;   // host table; the CUDA library repoints this at its device copy
+    t->pad_ = 0;
     for (int i = 0; i < 256; i++) t->cyclic_syn[i] = P25_CYCLIC16_SYN[i];
     for (int i = 0; i < 16; i++) {
         t->ham15_syn[i] = P25_HAMMING15_SYN[i];

@@ -50,6 +50,7 @@ struct p25cu_ctx {
     unsigned* d_offsets;       // [S + 2]: exclusive offsets, total, overflow flag
     unsigned* d_stats;
     P25DevTables* d_tables;
+    uint32_t* d_golay;         // Golay(23,12) syndrome table (referenced from d_tables)
     p25cu_event* h_events;     // pinned staging for polls (grown on demand)
     size_t h_events_cap;
     unsigned long long a_abs;  // input samples consumed per stream
@@ -102,6 +103,7 @@ extern "C" void p25cu_destroy(p25cu_ctx* ctx) {
     cudaFree(ctx->d_offsets);
     cudaFree(ctx->d_stats);
     cudaFree(ctx->d_tables);
+    cudaFree(ctx->d_golay);
     cudaFree(ctx->d_pfb_taps);
     cudaFree(ctx->d_twiddle);
     cudaFree(ctx->d_y);
@@ -181,7 +183,10 @@ static int create_impl(p25cu_ctx* ctx) {
         if (!t) return fail_arg(ctx, "out of host memory");
         memset(t, 0, sizeof *t);
         p25_fill_tables(t);
-        cudaError_t e = cudaMemcpy(ctx->d_tables, t, sizeof *t, cudaMemcpyHostToDevice);
+        cudaError_t e = cudaMalloc(&ctx->d_golay, sizeof(P25_GOLAY23_SYN));
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->d_golay, P25_GOLAY23_SYN, sizeof(P25_GOLAY23_SYN), cudaMemcpyHostToDevice);
+        t->golay_syn = ctx->d_golay;
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tables, t, sizeof *t, cudaMemcpyHostToDevice);
         delete t;
         CK(e);
     }
