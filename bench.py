@@ -50,6 +50,55 @@ METRIC = "Msamples/s IQ demod+decode (real-time P25 channels = baseband samples/
 ALG_BYTES_PER_SAMPLE = 8.0 + 4.0 / DECIM     # SURVEY.md section 8(d), DESIGN.md section 4
 
 
+class Workload:
+    """cfg2 (default, the configuration the metric is quoted on): 1,024 cf32 2.4 MS/s streams per GPU, weak scaling.
+    cfg5 (BASELINE.json configs[4]): 65,536 streams in the reference's own format (u8 IQ at 240 kS/s, /5), sharded
+    over the ranks (strong scaling), generated on the device from 16 seeded transmissions."""
+
+    def __init__(self, name: str, world: int):
+        self.name = name
+        if name == "cfg5":
+            assert 65536 % world == 0
+            self.streams, self.fs, self.decim, self.fmt, self.n, self.scaling = 65536 // world, 240_000, 5, "u8", 36_000, "strong"
+            self.bps = 2
+            self.kernel = "fast5::p25_ddc5_fm_kernel<u8> (/5)"
+            self.desc = (f"configs[4]: 65,536 synthetic P25 control-channel streams in the reference's own format (u8 IQ, "
+                         f"240 kS/s, /5 -> 48 kHz), {self.streams} per GPU, 36000 samples (150 ms) per stream per step, "
+                         "C4FM demod + frame sync + NID/TSBK decode")
+        else:
+            self.streams, self.fs, self.decim, self.fmt, self.n, self.scaling = STREAMS_PER_GPU, FS, DECIM, "cf32", N_PER_STEP, "weak"
+            self.bps = 8
+            self.kernel = "fast::p25_ddc_fm_stream_kernel (cf32, /50)"
+            self.desc = ("configs[1]: 1024 synthetic P25 control-channel IQ streams per GPU, cf32 2.4 MS/s, 360000 samples "
+                         "(150 ms) per stream per step, /50 -> 48 kHz, C4FM demod + frame sync + NID/TSBK decode")
+        self.alg_bytes_per_sample = self.bps + 4.0 / self.decim
+
+    def config(self, world: int):
+        gb = self.streams * self.n * self.bps / 1e9
+        return {"workload": self.desc, "streams_per_gpu": self.streams, "samples_per_stream_per_step": self.n,
+                "sample_rate": self.fs, "decimation": self.decim, "input_format": self.fmt, "snr_db": 20,
+                "l2_policy": f"inputs ({gb:.2f} GB/step) larger than L2",
+                "parallelism": f"streams sharded over {world} GPU(s), no collective"}
+
+    def base(self):
+        from tools import p25tx as tx
+        rows = []
+        for b in range(N_BASE):
+            st = tx.control_channel(1000 + b, 2, lead_idle=0)
+            assert len(st.dibits) * 10 * self.decim == self.n
+            iq = tx.modulate_iq_periodic(st.dibits, self.fs, snr_db=20.0, cfo_cycles=3 * (b - N_BASE // 2), seed=b)
+            rows.append(tx.iq_to_u8(iq).reshape(self.n, 2) if self.fmt == "u8" else iq.view(np.float32).reshape(self.n, 2))
+        return np.stack(rows)
+
+    def oracle_input(self, n_streams: int):
+        """Host array of the first n_streams streams in the oracle's layout."""
+        base = self.base()
+        out = np.empty((n_streams,) + base.shape[1:], dtype=base.dtype)
+        for s in range(n_streams):
+            out[s] = np.roll(base[s % N_BASE], -((s // N_BASE) * 5003 % self.n), axis=0)
+        return out
+
+
 def make_base_streams():
     from tools import p25tx as tx
     base = []
@@ -118,9 +167,12 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_arm(steps: int, warmup: int, iq: np.ndarray | None = None):
+def cpu_arm(steps: int, warmup: int, iq: np.ndarray | None = None, wl: "Workload | None" = None):
     """Oracle CPU implementation on the host cores (rank 0 only).  Returns (Msamples/s, ms/step, info).
-    Each step is the full 1,024-stream batch of the GPU arm (about 8 core-seconds of work)."""
+    Each step is the full 1,024-stream batch of the GPU arm (about 8 core-seconds of work); for cfg5 a bounded
+    sample of 4,096 of the 65,536 streams."""
+    if wl is not None and wl.name == "cfg5":
+        return cpu_arm_cfg5(steps, warmup, wl)
     from oracle import pyoracle as po
     try:
         po.build(native=True)
@@ -150,6 +202,32 @@ def cpu_arm(steps: int, warmup: int, iq: np.ndarray | None = None):
     return val, ms, info
 
 
+def cpu_arm_cfg5(steps: int, warmup: int, wl: "Workload"):
+    from oracle import pyoracle as po
+    try:
+        po.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    cores = os.cpu_count() or 1
+    po.lib(native).p25o_set_always_correlate(1)
+    n_streams = 4096
+    iq = wl.oracle_input(n_streams)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        total, _, _ = po.batch_run(po.FMT_U8, False, iq, n_streams, wl.n, cores, native=native)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        assert total >= 3 * n_streams
+    ms = 1e3 * float(np.mean(times))
+    val = n_streams * wl.n / (ms * 1e-3) / 1e6
+    return val, ms, {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port",
+                     "sample": f"{n_streams} of the 65536 streams x {wl.n} u8 samples per step ({steps} timed step(s)), {cores} "
+                               f"threads, oracle built {'-march=native' if native else '-march=x86-64-v3'}; the Rust reference cannot be built here"}
+
+
 def config_dict(n_gpus: int):
     return {"workload": "configs[1]: 1024 synthetic P25 control-channel IQ streams per GPU, cf32 2.4 MS/s, 360000 samples "
                         "(150 ms) per stream per step, /50 -> 48 kHz, C4FM demod + frame sync + NID/TSBK decode",
@@ -162,12 +240,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, ms, info = cpu_arm(args.steps, args.warmup)
+    wl = Workload(args.workload, max(1, args.gpus))
+    val, ms, info = cpu_arm(args.steps, args.warmup, wl=wl)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus), "cpu_baseline": info,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": wl.config(args.gpus), "cpu_baseline": info,
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "realtime_channels": val * 1e6 / DECIM / 48000.0, "gpu_launches": 0}
+            "realtime_channels": val * 1e6 / wl.decim / 48000.0, "gpu_launches": 0}
     print(json.dumps(line))
 
 
@@ -184,13 +263,17 @@ def run_b200(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    S, n, K, W = STREAMS_PER_GPU, N_PER_STEP, args.steps, max(args.warmup, 3)
-    base = make_base_streams()
-    host = torch.empty((S, n, 2), dtype=torch.float32, pin_memory=True)
-    fill_streams(host.numpy().view(np.complex64).reshape(S, n), base, rank * S)
-    dev = host.cuda(non_blocking=False)
+    wl = Workload(args.workload, world)
+    S, n, K, W = wl.streams, wl.n, args.steps, max(args.warmup, 3)
+    # streams = circular shifts of N_BASE seeded transmissions, tiled on the device, then
+    # mirrored into pinned host memory for the end-to-end leg
+    from tools.shape_bench import tile_on_device
+    dev = tile_on_device(torch.from_numpy(wl.base()).cuda(), S, first=rank * S)
+    host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
+    host.copy_(dev)
     slots = 8 * (W + K) + 32
-    ctx = p25.Context(S, fmt=p25.FMT_CF32_IQ, decimation=DECIM, max_chunk_samples=n, device=local, event_slots=slots)
+    ctx = p25.Context(S, fmt=p25.FMT_U8_IQ if wl.fmt == "u8" else p25.FMT_CF32_IQ, decimation=wl.decim, max_chunk_samples=n,
+                      device=local, event_slots=slots)
     stream = torch.cuda.ExternalStream(ctx.cuda_stream, device=local)
 
     def barrier():
@@ -277,23 +360,23 @@ def run_b200(args):
     e2e_value = total_samples / (e2e_ms * 1e-3) / 1e6
 
     peak, peak_src = measured_peak_gbs()
-    alg_bytes = S * n * ALG_BYTES_PER_SAMPLE
+    alg_bytes = S * n * wl.alg_bytes_per_sample
     achieved = alg_bytes / (ddc_ms * 1e-3) / 1e9
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": config_dict(world),
-            "realtime_channels": value * 1e6 / DECIM / 48000.0,
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": S * n * 8, "d2h_bytes_per_step": d2h // K,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": wl.config(world),
+            "realtime_channels": value * 1e6 / wl.decim / 48000.0,
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": S * n * wl.bps, "d2h_bytes_per_step": d2h // K,
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": int(launches),
             "kernels": {"p25_ddc_fm_kernel_ms": ddc_ms, "step_ms": dev_ms / K, "host_enqueue_ms_per_step": enqueue_ms / K,
                         "serialised": {"p25_ddc_fm_kernel_ms": ddc_serial_ms, "p25_walk_kernel_ms": walk_ms}},
-            "roofline": {"kernel": "fast::p25_ddc_fm_stream_kernel (cf32, /50)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": wl.kernel, "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": sampler.result(), "events_checked": {"tsbk": n_tsbk, "errors": n_err}}
     try:
-        with open(os.path.join(ROOT, "profiles", "ddc_fm_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "ddc_fm_traffic.json" if wl.name != "cfg5" else "ddc5_u8_traffic.json")) as f:
             tr = json.load(f)
             line["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
     except Exception:
@@ -301,7 +384,10 @@ def run_b200(args):
     ctx.close()
     if rank == 0:
         if world == 1 and not args.no_cpu:
-            _, _, info = cpu_arm(1, 0, host.numpy().view(np.complex64).reshape(S, n))
+            if wl.name == "cfg5":
+                _, _, info = cpu_arm(1, 0, wl=wl)
+            else:
+                _, _, info = cpu_arm(1, 0, host.numpy().view(np.complex64).reshape(S, n))
             line["cpu_baseline"] = info
         print(json.dumps(line))
     if dist is not None:
@@ -315,6 +401,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
+                    help="cfg2 (default): 1,024 cf32 2.4 MS/s streams per GPU; cfg5: 65,536 u8 240 kS/s streams over all GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

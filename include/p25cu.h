@@ -152,7 +152,7 @@ int p25cu_get_stats(p25cu_ctx* ctx, uint32_t stream, p25cu_stats* out, int clear
  * as void*), a wait for it, and the number of kernel launches issued so far. */
 void* p25cu_cuda_stream(p25cu_ctx* ctx);
 int p25cu_sync(p25cu_ctx* ctx);
-/* Pipelining of consecutive chunks (default on): the decode walker of chunk k runs on a second CUDA stream
+/* Pipelining of consecutive chunks (default: on for decimation 50, off otherwise): the decode walker of chunk k runs on a second CUDA stream
  * concurrently with the demod kernel of chunk k+1 (double-buffered baseband).  Results do not depend on it.
  * on = 0 serialises both kernels on the stream returned by p25cu_cuda_stream (per-kernel timing). */
 int p25cu_set_overlap(p25cu_ctx* ctx, int on);

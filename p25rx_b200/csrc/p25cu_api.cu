@@ -142,7 +142,9 @@ static int create_impl(p25cu_ctx* ctx) {
         CK(cudaEventCreateWithFlags(&ctx->ev_bb_ready[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_bb_free[i], cudaEventDisableTiming));
     }
-    ctx->overlap = 1;
+    // The walker runs beside the next chunk's demod kernel only where that kernel is HBM-bound (/50: issue slots are
+    // free); the /5 and channelizer kernels are issue-bound themselves and co-running only slows both (measured).
+    ctx->overlap = cfg.decimation == 50 ? 1 : 0;
     const size_t S = cfg.n_streams;
     const bool wide = cfg.decimation == (int)p25cu_pfb_decimation();
     ctx->n_captures = wide ? cfg.n_streams / p25cu_pfb_channels() : 0;
