@@ -405,3 +405,58 @@ def test_channelizer_spectra_baseband_and_events(p25, oracle):
     assert sorted(set(int(s) for s in good["stream"])) == sorted(occupied)
     assert np.count_nonzero(ev["kind"] == p25.EV_TSBK) == 6 * len(occupied)
     ctx.close()
+
+
+# ------------------------------------------------------------------ the reference's own driver shapes (host mirrors)
+def test_replay_receiver_reads_baseband_files_like_replay_rs(p25, oracle, tmp_path):
+    """src/replay.rs:26-57: f32le 48 kHz files read in 32,768-byte blocks, VoiceFrames handed to the audio sink,
+    stats merged.  Three recordings replayed at once against the oracle fed the same files."""
+    from p25rx_b200 import consumers as co
+    files = []
+    for s in range(3):
+        st = tx.traffic_channel(900 + s, 2) if s != 1 else tx.control_channel(900 + s, 5)
+        bb, _ = tx.baseband_48k(st.dibits, snr_db=14, seed=s)
+        path = tmp_path / f"rec{s}.f32"
+        with open(path, "wb") as f:
+            co.write_baseband(f, bb[:60000])
+        files.append(path)
+    voice = []
+    rr = p25.ReplayReceiver(n_streams=3, on_voice_frame=lambda e: voice.append((int(e["stream"]), int(e["sample"]))))
+    handles = [open(pth, "rb") for pth in files]
+    got = rr.replay(handles)
+    got = got[np.lexsort((got["sample"], got["stream"]))]
+    ref = []
+    for s, pth in enumerate(files):
+        o = oracle.MessageReceiver(stream=s)
+        with open(pth, "rb") as f:
+            for blk in co.read_baseband_blocks(f):
+                ref.append(o.feed(blk))
+    ref = np.concatenate(ref)
+    ref = ref[np.lexsort((ref["sample"], ref["stream"]))]
+    assert events_key(got) == events_key(ref)
+    assert len(voice) == np.count_nonzero(ref["kind"] == p25.EV_VOICE_FRAME) > 30
+    rr.ctx.close()
+
+
+def test_demod_task_reports_power_every_fourth_chunk(p25, oracle):
+    """src/demod.rs:62-119 with the SDR's 32,768-byte chunks (src/consts.rs:6): baseband every chunk, signal power on
+    every 4th (Throttler::new(4), src/demod.rs:67, :95-101), equal to the oracle's power_dbm (src/demod.rs:123-134)."""
+    st = tx.control_channel(77, 6)
+    raw = tx.iq_to_u8(tx.modulate_iq(st.dibits, 240_000, snr_db=25, seed=2, amplitude=0.3))
+    n_chunks = len(raw) // 32768
+    assert n_chunks >= 9
+    ctx = p25.Context(2, fmt=p25.FMT_U8_IQ, decimation=5, max_chunk_samples=16384)
+    task = p25.DemodTask(ctx)
+    chain = oracle.DemodChain(oracle.FMT_U8, False)
+    lens = []
+    for i in range(9):
+        chunk = raw[i * 32768:(i + 1) * 32768]
+        bb, pw = task.run_chunk(np.stack([chunk, chunk]))
+        ref, pref = chain.feed(chunk, want_power=True)
+        lens.append(bb.shape[1])
+        assert bb.shape[1] == len(ref) and np.max(np.abs(bb[0] - ref)) < BB_TOL and np.array_equal(bb[0], bb[1])
+        assert (pw is not None) == (i % 4 == 0)
+        if pw is not None:
+            assert abs(pw[0] - pref) < 1e-2 and abs(pw[0] - (30 + 10 * np.log10(0.09))) < 1.0
+    assert set(lens) == {3276, 3277} and sum(lens) == 9 * 16384 // 5      # phase carried across chunks (SURVEY 8a a2)
+    ctx.close()
