@@ -871,6 +871,248 @@ __global__ void __launch_bounds__(K<FMT>::NT) p25_ddc5_fm_kernel(const DdcParams
 
 }  // namespace fast5
 
+
+// =====================================================================================================
+// Warp-autonomous variant of the /5 fast path for u8 input (the reference's own format, where the FP32 pipe and
+// the issue slots, not HBM, are the limit).  The tile kernel above spends a third of its stall samples at CTA
+// barriers whose stages keep only part of the CTA busy; here every warp is its own pipeline and the only
+// synchronisation is __syncwarp:
+//   * a warp walks a contiguous share of the flattened (stream, iteration) space, 124 outputs per iteration
+//     (31 lanes x 4; lane 31 only contributes its inputs' partial sums to lane 30), entering each stream or
+//     share with one discarded warm-up iteration, so the carried FIR histories live in per-warp shared memory;
+//   * lane 0 streams the raw 1.3 KB input slices with TMA bulk copies into a per-warp two-stage ring;
+//   * decimator outputs are kept as rows of four (two 16-byte halves in two arrays): a lane's 44-sample channel
+//     filter window is then 22 conflict-free LDS.128 of consecutive rows;
+//   * the channel filter's four outputs stay in registers for the discriminator (the previous sample arrives
+//     by shuffle), only the discriminator rows go back to shared memory for the boxcar; stores are 16 bytes
+//     per lane, 496 contiguous bytes per warp.
+// =====================================================================================================
+namespace w5 {
+
+using fast::cfma;
+using fast::mbar_init;
+using fast::mbar_expect_tx;
+using fast::mbar_wait;
+using fast::tma_load_1d;
+using fast5::add2;
+using fast5::disc_atan2;
+using fast5::load_u8;
+
+constexpr int R = 4;                        // outputs per lane
+constexpr int NOUT = 31 * R;                // 124 outputs per warp iteration
+constexpr int XNEW = 5 * NOUT;              // 620 fresh input samples per iteration
+constexpr int XN = 32 * 5 * R;              // 640 samples read (the ghost lane's 20 included)
+constexpr int AL = 8, ES = 2;
+constexpr int XLEN = (XN + 2 * AL - 2) / AL * AL;     // 648
+constexpr int XBYTES = (XLEN * ES + 127) / 128 * 128; // 1408
+constexpr int WARPS = 4;                    // per CTA
+constexpr int HROWS = (P25_TAPS_CHAN - 1) / R;        // 10 history rows of the decimator output
+constexpr int DROWS = 3;                    // history rows of the discriminator output (>= 9 samples)
+static_assert((P25_TAPS_CHAN - 1) % R == 0 && DROWS * R >= P25_BOXCAR - 1, "history rows");
+
+struct __align__(128) WarpSm {
+    unsigned char xs[2][XBYTES];
+    float4 ydA[HROWS + 32], ydB[HROWS + 32];    // row i: (yd[4i], yd[4i+1]) | (yd[4i+2], yd[4i+3])
+    float4 d4[DROWS + 32];
+    unsigned long long full[2];
+};
+
+// bulk copy of the slice whose first input has logical index l0 (tail ++ chunk); 32-bit index arithmetic, the slice
+// that still overlaps the carried tail (first iterations of a chunk only) takes the two-copy path
+__device__ __forceinline__ void issue_slice(WarpSm& sm, int stage, int ht, int lend, const unsigned char* tail,
+                                            const unsigned char* chunk, int l0) {
+    const int la = l0 & ~(AL - 1);
+    const int lb = min(la + XLEN, lend);
+    if (la >= ht) {
+        const unsigned bytes = (unsigned)(lb - la) * ES;
+        mbar_expect_tx(&sm.full[stage], bytes);
+        tma_load_1d(&sm.xs[stage][0], chunk + (size_t)(la - ht) * ES, bytes, &sm.full[stage]);
+        return;
+    }
+    const int t1 = min(lb, ht);
+    const unsigned nt = (unsigned)(t1 - la), nc = (unsigned)(lb - t1);
+    mbar_expect_tx(&sm.full[stage], (nt + nc) * ES);
+    tma_load_1d(&sm.xs[stage][0], tail + (size_t)la * ES, nt * ES, &sm.full[stage]);
+    if (nc) tma_load_1d(&sm.xs[stage][nt * ES], chunk, nc * ES, &sm.full[stage]);
+}
+
+__global__ void __launch_bounds__(32 * WARPS, 8) p25_ddc5_warp_kernel(const DdcParams p, const unsigned its_per_stream,
+                                                                      const float dc, const float pw_scale) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSm& sm = reinterpret_cast<WarpSm*>(smem_raw)[warp];
+    if (lane == 0) {
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = lane; i < HROWS + 32; i += 32) sm.ydA[i] = sm.ydB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < DROWS + 32; i += 32) sm.d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+
+    // this warp's share [b0, b1) of the flattened (stream, iteration) space, walked piece by piece: a piece is a run of
+    // stored iterations of one stream preceded by one warm-up iteration (iteration it_first - 1; -1 = the inputs just
+    // before the chunk, served by the carried tail) that only rebuilds the filter histories
+    const unsigned gw = blockIdx.x * WARPS + warp, GW = gridDim.x * WARPS;
+    const unsigned long long total = (unsigned long long)p.n_streams * its_per_stream;
+    const unsigned long long b0 = total * gw / GW, b1 = total * (gw + 1ull) / GW;
+    if (b0 >= b1) return;
+    const int ips = (int)its_per_stream, ht = (int)p.ht, lend = (int)p.ht + (int)p.n, n_out = (int)p.n_out;
+    const size_t row_bytes = (size_t)p.n * ES, tail_bytes = (size_t)p.ht * ES;
+    const int l_base = (int)(5 * (long long)p.m0 - (long long)p.a0) - 20 + ht;   // logical index of iteration 0's first input
+    const bool want_pw = p.power_sum != nullptr;
+    unsigned s = (unsigned)(b0 / its_per_stream);
+    int it_first = (int)(b0 % its_per_stream);
+    unsigned left = (unsigned)(b1 - b0);                   // stored iterations still to do
+    const unsigned char* chunk = (const unsigned char*)p.iq + s * row_bytes;
+    const unsigned char* tail = (const unsigned char*)p.tail_in + s * tail_bytes;
+    if (lane == 0) {                                        // warm-up and first stored iteration of the first piece
+        issue_slice(sm, 0, ht, lend, tail, chunk, l_base + XNEW * (it_first - 1));
+        issue_slice(sm, 1, ht, lend, tail, chunk, l_base + XNEW * it_first);
+    }
+    float2 c_carry = make_float2(0.f, 0.f);
+    unsigned use = 0;
+
+    while (left) {
+      const int n_st = min(ips - it_first, (int)left);     // stored iterations of this piece
+      const int npiece = n_st + 1;
+      left -= (unsigned)n_st;
+      float* const out_lane = p.bb + (size_t)s * p.row_stride + P25CU_BB_HIST + R * lane;
+      float pw = 0.f;
+      for (int j = 0; j < npiece; j++, use++) {
+        const int it = it_first - 1 + j;
+        const int stage = use & 1;
+        const int skew = (l_base + XNEW * it) & (AL - 1);
+        const int nv = j ? min(n_out - NOUT * it, NOUT) : 0;     // j = 0 is the warm-up: nothing is stored
+        mbar_wait(&sm.full[stage], (use >> 1) & 1);
+
+        // ---- /5 decimator (same arithmetic as the tile kernel): lane owns inputs [20 lane, 20 lane + 20)
+        float2 own[R];
+        {
+            float2 x[5 * R];
+            const int s0 = skew + 5 * R * lane;
+            const unsigned* wp = reinterpret_cast<const unsigned*>(sm.xs[stage]) + (s0 >> 1);
+            if (s0 & 1) load_u8<R, true>(wp, x);
+            else load_u8<R, false>(wp, x);
+            float2 lft[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                own[r] = make_float2(0.f, 0.f);
+                lft[r] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = P25_TAPS_DECIM - 1; k >= 0; k--) {
+                    const int idx = 5 * r + (P25_TAPS_DECIM - 1) - k;
+                    if (idx < 5 * R) own[r] = cfma(c_taps_decim[k], x[idx], own[r]);
+                    else lft[r] = cfma(c_taps_decim[k], x[idx - 5 * R], lft[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (5 * r + (P25_TAPS_DECIM - 1) >= 5 * R) {
+                    own[r].x += __shfl_down_sync(0xFFFFFFFFu, lft[r].x, 1);
+                    own[r].y += __shfl_down_sync(0xFFFFFFFFu, lft[r].y, 1);
+                }
+            }
+        }
+        sm.ydA[HROWS + lane] = make_float4(own[0].x, own[0].y, own[1].x, own[1].y);   // lane 31's row is never read
+        sm.ydB[HROWS + lane] = make_float4(own[2].x, own[2].y, own[3].x, own[3].y);
+        __syncwarp();                                                                 // S1: xs[stage] consumed, rows visible
+        if (lane == 0) {                                    // prefetch two iterations ahead (possibly into the next piece)
+            if (j + 2 < npiece) issue_slice(sm, stage, ht, lend, tail, chunk, l_base + XNEW * (it + 2));
+            else if (left) issue_slice(sm, stage, ht, lend, tail + tail_bytes, chunk + row_bytes, l_base + XNEW * (j + 1 - npiece));
+        }
+
+        // ---- channel-select FIR: outputs 4 lane + r, window = rows lane .. lane + 10 (44 samples, s = 40 + r - k)
+        float2 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = make_float2(dc, dc);
+#pragma unroll
+        for (int t = 0; t <= HROWS; t++) {
+            const float4 va = sm.ydA[lane + t], vb = sm.ydB[lane + t];
+            const float2 xs4[4] = {make_float2(va.x, va.y), make_float2(va.z, va.w), make_float2(vb.x, vb.y), make_float2(vb.z, vb.w)};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int k = (P25_TAPS_CHAN - 1) + r - (4 * t + q);
+                    if (k >= 0 && k < P25_TAPS_CHAN) acc[r] = cfma(c_taps_chan[k], xs4[q], acc[r]);
+                }
+            }
+        }
+        // ---- FM discriminator on the four outputs in registers; the sample before comes from the lane below
+        float2 prev;
+        prev.x = __shfl_up_sync(0xFFFFFFFFu, acc[R - 1].x, 1);
+        prev.y = __shfl_up_sync(0xFFFFFFFFu, acc[R - 1].y, 1);
+        if (lane == 0) prev = c_carry;
+        c_carry.x = __shfl_sync(0xFFFFFFFFu, acc[R - 1].x, 30);
+        c_carry.y = __shfl_sync(0xFFFFFFFFu, acc[R - 1].y, 30);
+        float dd[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float2 cu = acc[r];
+            const float re = cu.x * prev.x + cu.y * prev.y;
+            const float im = cu.y * prev.x - cu.x * prev.y;
+            dd[r] = disc_atan2(im, re) * P25_FM_GAIN;
+            if (want_pw && R * lane + r < nv) pw += cu.x * cu.x + cu.y * cu.y;
+            prev = cu;
+        }
+        sm.d4[DROWS + lane] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+        __syncwarp();                                                                 // S2
+
+        // ---- boxcar over d[o - 9 .. o], o = 4 lane + r: rows lane .. lane + 2 hold d[4 lane - 12 .. 4 lane - 1]
+        {
+            const float a = sm.d4[lane].w;
+            const float4 b = sm.d4[lane + 1], c4 = sm.d4[lane + 2];
+            float s0 = a + b.x;
+            s0 += b.y; s0 += b.z; s0 += b.w; s0 += c4.x; s0 += c4.y; s0 += c4.z; s0 += c4.w; s0 += dd[0];
+            const float s1 = (s0 - a) + dd[1], s2 = (s1 - b.x) + dd[2], s3 = (s2 - b.y) + dd[3];
+            const float kk = 1.0f / P25_BOXCAR;
+            const int o0 = R * lane;
+            if (o0 < nv) {
+                float* out = out_lane + NOUT * it;
+                if (o0 + 3 < nv) *reinterpret_cast<float4*>(out) = make_float4(s0 * kk, s1 * kk, s2 * kk, s3 * kk);
+                else {
+                    out[0] = s0 * kk;
+                    if (o0 + 1 < nv) out[1] = s1 * kk;
+                    if (o0 + 2 < nv) out[2] = s2 * kk;
+                }
+            }
+        }
+        // ---- roll the histories: the last 10 decimator rows and 3 discriminator rows move to the front
+        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra, rd = ra;
+        if (lane < HROWS) {
+            ra = sm.ydA[31 + lane];
+            rb = sm.ydB[31 + lane];
+        }
+        if (lane < DROWS) rd = sm.d4[31 + lane];
+        __syncwarp();                                                                 // S3
+        if (lane < HROWS) {
+            sm.ydA[lane] = ra;
+            sm.ydB[lane] = rb;
+        }
+        if (lane < DROWS) sm.d4[lane] = rd;
+
+      }
+      // ---- end of the piece: flush power, carry the raw input tail when the stream's chunk is complete, next stream
+      if (want_pw) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) pw += __shfl_xor_sync(0xFFFFFFFFu, pw, o);
+          if (lane == 0) atomicAdd(p.power_sum + s, pw * pw_scale);
+      }
+      if (it_first + n_st == ips) {
+          const uint4* src = reinterpret_cast<const uint4*>(chunk + ((size_t)p.n - p.ht) * ES);
+          uint4* dst = reinterpret_cast<uint4*>((unsigned char*)p.tail_out + s * tail_bytes);
+          for (int i = lane; i < (int)(tail_bytes / 16); i += 32) dst[i] = src[i];
+      }
+      s++;
+      it_first = 0;
+      chunk += row_bytes;
+      tail += tail_bytes;
+    }
+}
+
+}  // namespace w5
+
 unsigned p25cu_ddc_tail_len(int decimation) { return decimation == 50 ? Cfg<true>::HT : Cfg<false>::HT; }
 
 cudaError_t p25cu_ddc_upload_taps() {
@@ -943,8 +1185,39 @@ static cudaError_t launch_fast5(const DdcParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+static cudaError_t launch_w5(const DdcParams& p, cudaStream_t st) {
+    static int grid_cache = 0;
+    auto kern = w5::p25_ddc5_warp_kernel;
+    const size_t smem = sizeof(w5::WarpSm) * w5::WARPS;
+    if (!grid_cache) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int dev = 0, n_sm = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * w5::WARPS, smem);
+        if (e != cudaSuccess) return e;
+        grid_cache = n_sm * (per_sm > 0 ? per_sm : 1);
+    }
+    const unsigned ips = (p.n_out + w5::NOUT - 1) / w5::NOUT;
+    const unsigned long long total = (unsigned long long)p.n_streams * ips;
+    unsigned long long want = (total + 3) / 4;                 // at least ~4 iterations per warp (one warm-up each)
+    want = (want + w5::WARPS - 1) / w5::WARPS;
+    const unsigned grid = want < (unsigned long long)grid_cache ? (unsigned)(want ? want : 1) : (unsigned)grid_cache;
+    double gd = 0.0, gc = 0.0;
+    for (int k = 0; k < P25_TAPS_DECIM; k++) gd += (double)P25_TAPS_DECIM_H[k];
+    for (int k = 0; k < P25_TAPS_CHAN; k++) gc += (double)P25_TAPS_CHAN_H[k];
+    kern<<<grid, 32 * w5::WARPS, smem, st>>>(p, ips, (float)(0.5 * gd * gc), (float)(1.0 / (127.5 * 127.5)));
+    return cudaGetLastError();
+}
+
+int p25cu_ddc5_variant = 1;   // 1: warp-autonomous kernel for u8 (default), 0: tile kernel (kept for cf32 and for A/B timing)
+
 cudaError_t p25cu_launch_ddc(const DdcParams& p, int format, int decimation, cudaStream_t st) {
     if (p.n_out == 0 && p.n == 0) return cudaSuccess;
+    if (decimation == 5 && format == P25CU_FMT_U8_IQ && p25cu_ddc5_variant == 1 && p.aligned16 && p.n_out > 0 && p.a0 >= p.ht &&
+        p.n >= p.ht && p.ht == (unsigned)Cfg<false>::HT)
+        return launch_w5(p, st);
     // /5 fast path: aligned rows, the whole history inside the stream (no implicit zeros), chunk at least one tail long
     if (decimation == 5 && p.aligned16 && p.n_out > 0 && p.a0 >= p.ht && p.n >= p.ht && p.ht == (unsigned)Cfg<false>::HT)
         return format == P25CU_FMT_CF32_IQ ? launch_fast5<P25CU_FMT_CF32_IQ>(p, st) : launch_fast5<P25CU_FMT_U8_IQ>(p, st);

@@ -45,6 +45,16 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 mul_i(float2 a) { return make_float2(-a.y, a.x); }     // a * (+i)
+// acc += h * x on both components: one FFMA2
+__device__ __forceinline__ float2 cfma(float h, float2 x, float2 acc) {
+    unsigned long long r;
+    const float2 hh = make_float2(h, h);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&hh)), "l"(*reinterpret_cast<const unsigned long long*>(&x)),
+          "l"(*reinterpret_cast<const unsigned long long*>(&acc)));
+    return *reinterpret_cast<float2*>(&r);
+}
 
 // 8-point DFT with the + sign: w[q] = sum_r v[r] exp(+2 pi i r q / 8), in place
 __device__ __forceinline__ void dft8(float2 (&v)[8]) {
@@ -129,10 +139,7 @@ __global__ void __launch_bounds__(NT) p25_pfb_kernel(const PfbParams p) {
             float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
             for (int pp = 0; pp < P; pp++) {
-                const float hh = __ldg(p.taps + r + N * pp);
-                const float2 x = sm.xw[e - r - N * pp];
-                acc.x = fmaf(hh, x.x, acc.x);
-                acc.y = fmaf(hh, x.y, acc.y);
+                acc = cfma(__ldg(p.taps + r + N * pp), sm.xw[e - r - N * pp], acc);
             }
             int q = r - nm_mod;
             if (q < 0) q += N;
@@ -235,10 +242,7 @@ __global__ void __launch_bounds__(256) p25_chan_fm_kernel(const ChanParams p) {
 #pragma unroll
             for (int r = 0; r < RC; r++) {
                 const int k = HC - i + r;
-                if (k >= 0 && k <= HC) {
-                    acc[r].x = fmaf(c_chan[k], x.x, acc[r].x);
-                    acc[r].y = fmaf(c_chan[k], x.y, acc[r].y);
-                }
+                if (k >= 0 && k <= HC) acc[r] = cfma(c_chan[k], x, acc[r]);
             }
         }
 #pragma unroll

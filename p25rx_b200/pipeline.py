@@ -215,14 +215,18 @@ class ReplayReceiver:
         self.events: list[np.ndarray] = []
 
     def replay(self, streams) -> np.ndarray:
-        """streams: list of binary file objects (one per stream).  Unlike src/replay.rs:36 a short final
-        read is fed at its true length (the reference re-feeds the stale tail of its buffer)."""
+        """streams: list of binary file objects (one per stream), read in 32,768-byte blocks (src/replay.rs:27).
+        Every feed carries the same number of samples for every stream (the C ABI's shape), so a stream's unread
+        remainder is kept for the next round; replay ends when the shortest recording ends.  Unlike src/replay.rs:36 a
+        short final read is fed at its true length (the reference re-feeds the stale tail of its buffer)."""
+        pend = [b"" for _ in streams]
         while True:
-            blocks = [f.read(self.READ_BYTES) for f in streams]
-            n = min(len(b) for b in blocks) // 4
+            pend = [p if len(p) >= self.READ_BYTES else p + f.read(self.READ_BYTES) for p, f in zip(pend, streams)]
+            n = min(min(len(p) for p in pend), self.READ_BYTES) // 4
             if n == 0:
                 break
-            chunk = np.stack([np.frombuffer(b[: 4 * n], dtype="<f4") for b in blocks])
+            chunk = np.stack([np.frombuffer(p[: 4 * n], dtype="<f4") for p in pend])
+            pend = [p[4 * n:] for p in pend]
             ev = self.msg.feed(chunk)
             if self.on_voice_frame is not None:
                 for e in ev[ev["kind"] == EV_VOICE_FRAME]:

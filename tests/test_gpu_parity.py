@@ -418,7 +418,7 @@ def test_replay_receiver_reads_baseband_files_like_replay_rs(p25, oracle, tmp_pa
         bb, _ = tx.baseband_48k(st.dibits, snr_db=14, seed=s)
         path = tmp_path / f"rec{s}.f32"
         with open(path, "wb") as f:
-            co.write_baseband(f, bb[:60000])
+            co.write_baseband(f, bb[:18000 + 1111 * s])      # unequal lengths: replay ends with the shortest recording
         files.append(path)
     voice = []
     rr = p25.ReplayReceiver(n_streams=3, on_voice_frame=lambda e: voice.append((int(e["stream"]), int(e["sample"]))))
@@ -429,19 +429,19 @@ def test_replay_receiver_reads_baseband_files_like_replay_rs(p25, oracle, tmp_pa
     for s, pth in enumerate(files):
         o = oracle.MessageReceiver(stream=s)
         with open(pth, "rb") as f:
-            for blk in co.read_baseband_blocks(f):
-                ref.append(o.feed(blk))
+            data = np.concatenate(list(co.read_baseband_blocks(f)))[:18000]
+        ref.append(o.feed(data))
     ref = np.concatenate(ref)
     ref = ref[np.lexsort((ref["sample"], ref["stream"]))]
     assert events_key(got) == events_key(ref)
-    assert len(voice) == np.count_nonzero(ref["kind"] == p25.EV_VOICE_FRAME) > 30
+    assert len(voice) == np.count_nonzero(ref["kind"] == p25.EV_VOICE_FRAME) > 10
     rr.ctx.close()
 
 
 def test_demod_task_reports_power_every_fourth_chunk(p25, oracle):
     """src/demod.rs:62-119 with the SDR's 32,768-byte chunks (src/consts.rs:6): baseband every chunk, signal power on
     every 4th (Throttler::new(4), src/demod.rs:67, :95-101), equal to the oracle's power_dbm (src/demod.rs:123-134)."""
-    st = tx.control_channel(77, 6)
+    st = tx.control_channel(77, 9)
     raw = tx.iq_to_u8(tx.modulate_iq(st.dibits, 240_000, snr_db=25, seed=2, amplitude=0.3))
     n_chunks = len(raw) // 32768
     assert n_chunks >= 9
