@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libp25cu.so")
+LIB_PATH = os.environ.get("P25CU_LIB") or os.path.join(HERE, "libp25cu.so")   # P25CU_LIB: A/B builds of the same library
 ABI_VERSION = 1
 
 FMT_U8_IQ, FMT_CF32_IQ = 0, 1

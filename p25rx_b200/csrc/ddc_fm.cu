@@ -936,7 +936,10 @@ __device__ __forceinline__ void issue_slice(WarpSm& sm, int stage, int ht, int l
     if (nc) tma_load_1d(&sm.xs[stage][nt * ES], chunk, nc * ES, &sm.full[stage]);
 }
 
-__global__ void __launch_bounds__(32 * WARPS, 8) p25_ddc5_warp_kernel(const DdcParams p, const unsigned its_per_stream,
+#ifndef W5_MINB
+#define W5_MINB 5
+#endif
+__global__ void __launch_bounds__(32 * WARPS, W5_MINB) p25_ddc5_warp_kernel(const DdcParams p, const unsigned its_per_stream,
                                                                       const float dc, const float pw_scale) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
