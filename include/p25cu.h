@@ -157,6 +157,11 @@ int p25cu_sync(p25cu_ctx* ctx);
  * on = 0 serialises both kernels on the stream returned by p25cu_cuda_stream (per-kernel timing). */
 int p25cu_set_overlap(p25cu_ctx* ctx, int on);
 uint64_t p25cu_launch_count(const p25cu_ctx* ctx);
+/* Demod-kernel timing: while enabled, every p25cu_demod / p25cu_process records a CUDA event pair on the launching
+ * stream right around its kernel launch(es) (after any wait for a baseband buffer), at most 128 launches.  Each call
+ * waits for the stream, returns the average duration and the number of launches recorded since the previous call,
+ * clears the record and sets the enable state. */
+int p25cu_demod_timing(p25cu_ctx* ctx, int enable, double* avg_ms, unsigned* count);
 /* Device pointer/row stride (in floats) of the baseband produced by the last p25cu_demod. */
 int p25cu_device_baseband(p25cu_ctx* ctx, const float** ptr, size_t* row_stride, size_t* n_out);
 

@@ -21,6 +21,8 @@
 // the only carried state is the raw input tail.
 //
 // HBM-bound by design: algorithmic traffic 8 + 4/D bytes per cf32 input sample.
+#include <stdlib.h>
+
 #include "p25cu_internal.cuh"
 
 __constant__ float c_taps_front[P25_TAPS_FRONT];
@@ -406,9 +408,21 @@ __device__ __forceinline__ void issue_block(Smem& sm, int stage, const DdcParams
     if (nc) tma_load_1d(&sm.xs[stage][cb - l0], chunk + (cb - ht), nc * 8u, &sm.full[stage]);
 }
 
-__global__ void __launch_bounds__(NT, 3) p25_ddc_fm_stream_kernel(const DdcParams p, const unsigned blocks_per_stream) {
+// Work distribution: the flattened (stream, block) space is split into a static part (n_static consecutive blocks per
+// CTA, no extra warm-ups) and a dynamic remainder handed out in DYN_CH-block tickets.  A CTA that becomes resident
+// late -- the previous chunk's walker CTAs still hold registers and shared memory on its SM -- simply draws fewer
+// tickets instead of stretching the whole launch (with a purely static split that tail cost ~9 % beside the walker).
+constexpr unsigned DYN_CH = 16;
+
+#ifndef DDC50_MAXREG
+#define DDC50_MAXREG 56
+#endif
+__global__ void __maxnreg__(DDC50_MAXREG) p25_ddc_fm_stream_kernel(const DdcParams p, const unsigned blocks_per_stream,
+                                                                  const unsigned n_static, const unsigned n_tickets,
+                                                                  const unsigned ticket_base) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    __shared__ unsigned s_ticket;
     const int tid = threadIdx.x;
 
     if (tid == 0) {
@@ -416,14 +430,24 @@ __global__ void __launch_bounds__(NT, 3) p25_ddc_fm_stream_kernel(const DdcParam
         mbar_init(&sm.full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // this CTA's share of the flattened (stream, block) space
     const unsigned long long total = (unsigned long long)p.n_streams * blocks_per_stream;
-    unsigned long long b = total * blockIdx.x / gridDim.x;
-    const unsigned long long b_end = total * (blockIdx.x + 1ull) / gridDim.x;
+    const unsigned long long dyn_begin = (unsigned long long)n_static * gridDim.x;
+    unsigned long long b = (unsigned long long)n_static * blockIdx.x;      // static share first
+    unsigned long long b_end = b + n_static;
     const long long M0 = (long long)p.m0, a0 = (long long)p.a0;
     unsigned use = 0;   // blocks consumed so far by this CTA: stage = use & 1, parity = (use >> 1) & 1
     __syncthreads();
 
+  for (;;) {
+    if (b >= b_end) {                                                       // draw the next ticket of the dynamic part
+        if (tid == 0) s_ticket = atomicAdd(p.work_counter, 1u) - ticket_base;
+        __syncthreads();
+        const unsigned c = s_ticket;
+        __syncthreads();
+        if (c >= n_tickets) break;
+        b = dyn_begin + (unsigned long long)c * DYN_CH;
+        b_end = b + DYN_CH < total ? b + DYN_CH : total;
+    }
     while (b < b_end) {
         const unsigned s = (unsigned)(b / blocks_per_stream);
         const unsigned it0 = (unsigned)(b % blocks_per_stream);
@@ -573,6 +597,7 @@ __global__ void __launch_bounds__(NT, 3) p25_ddc_fm_stream_kernel(const DdcParam
         }
         __syncthreads();
     }
+  }
 }
 
 }  // namespace fast
@@ -1150,12 +1175,19 @@ static cudaError_t launch_fast(const DdcParams& p, cudaStream_t st) {
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast::p25_ddc_fm_stream_kernel, fast::NT, smem);
         if (e != cudaSuccess) return e;
+        if (const char* ev = getenv("P25CU_DDC_CTAS")) per_sm = atoi(ev);   // A/B: CTAs per SM of the persistent grid
         grid_cache = n_sm * (per_sm > 0 ? per_sm : 1);
     }
     const unsigned bps = (p.n_out + fast::MB - 1) / fast::MB;
     const unsigned long long total = (unsigned long long)p.n_streams * bps;
     const unsigned grid = total < (unsigned long long)grid_cache ? (unsigned)total : (unsigned)grid_cache;
-    fast::p25_ddc_fm_stream_kernel<<<grid, fast::NT, smem, st>>>(p, bps);
+    // 7/8 of the blocks are split statically, the rest goes out in tickets; the ticket counter only ever grows, every
+    // launch consumes n_tickets + grid draws (each CTA stops at its first out-of-range ticket)
+    const unsigned n_static = (unsigned)(total / grid * 7 / 8);
+    const unsigned long long dyn = total - (unsigned long long)n_static * grid;
+    const unsigned n_tickets = (unsigned)((dyn + fast::DYN_CH - 1) / fast::DYN_CH);
+    fast::p25_ddc_fm_stream_kernel<<<grid, fast::NT, smem, st>>>(p, bps, n_static, n_tickets, *p.ticket_base);
+    *p.ticket_base += n_tickets + grid;
     return cudaGetLastError();
 }
 

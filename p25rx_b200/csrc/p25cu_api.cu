@@ -6,6 +6,7 @@
 // CUDA work or fails with an error code.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -44,6 +45,12 @@ struct p25cu_ctx {
     int bb_cur;                // buffer the next producer (demod / host baseband) writes
     int bb_last;               // buffer holding the newest undecoded baseband
     float* d_power;
+    unsigned* d_work;          // ticket counter of the /50 demod kernel (monotonic)
+    // optional per-launch timing of the demod kernel(s): event pairs recorded right around the launch
+    int timing;
+    unsigned n_timed;
+    cudaEvent_t tev[2 * 128];
+    unsigned ticket_base;
     WalkState* d_states;
     p25cu_event* d_slots;
     p25cu_event* d_dense;
@@ -97,6 +104,9 @@ extern "C" void p25cu_destroy(p25cu_ctx* ctx) {
     cudaFree(ctx->d_bb[0]);
     cudaFree(ctx->d_bb[1]);
     cudaFree(ctx->d_power);
+    cudaFree(ctx->d_work);
+    for (int i = 0; i < 2 * 128; i++)
+        if (ctx->tev[i]) cudaEventDestroy(ctx->tev[i]);
     cudaFree(ctx->d_states);
     cudaFree(ctx->d_slots);
     cudaFree(ctx->d_dense);
@@ -132,11 +142,13 @@ static int create_impl(p25cu_ctx* ctx) {
         return P25CU_ERR_CUDA;
     }
     ctx->n_sm = prop.multiProcessorCount;
-    {   // the HBM-bound demod kernel gets the SMs first; the latency-bound walker fills what is left
+    {   // stream priorities (A/B switch P25CU_WALK_PRIO: 0 = demod first, 1 = walker first, 2 = equal)
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi));
-        CK(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, lo));
+        const char* e = getenv("P25CU_WALK_PRIO");
+        const int mode = e ? atoi(e) : 0;
+        CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, mode == 1 ? lo : hi));
+        CK(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, mode == 0 ? lo : hi));
     }
     for (int i = 0; i < 2; i++) {
         CK(cudaEventCreateWithFlags(&ctx->ev_bb_ready[i], cudaEventDisableTiming));
@@ -145,6 +157,7 @@ static int create_impl(p25cu_ctx* ctx) {
     // The walker runs beside the next chunk's demod kernel only where that kernel is HBM-bound (/50: issue slots are
     // free); the /5 and channelizer kernels are issue-bound themselves and co-running only slows both (measured).
     ctx->overlap = cfg.decimation == 50 ? 1 : 0;
+    if (const char* e = getenv("P25CU_OVERLAP")) ctx->overlap = atoi(e) ? 1 : 0;   // A/B switch
     const size_t S = cfg.n_streams;
     const bool wide = cfg.decimation == (int)p25cu_pfb_decimation();
     ctx->n_captures = wide ? cfg.n_streams / p25cu_pfb_channels() : 0;
@@ -172,6 +185,8 @@ static int create_impl(p25cu_ctx* ctx) {
         CK(cudaMemsetAsync(ctx->d_bb[i], 0, S * ctx->row_stride * sizeof(float), ctx->stream));
     }
     CK(cudaMalloc(&ctx->d_power, S * sizeof(float)));
+    CK(cudaMalloc(&ctx->d_work, 64));
+    CK(cudaMemsetAsync(ctx->d_work, 0, 64, ctx->stream));
     CK(cudaMalloc(&ctx->d_states, S * sizeof(WalkState)));
     CK(cudaMemsetAsync(ctx->d_states, 0, S * sizeof(WalkState), ctx->stream));  // state SYNC, pos 0
     CK(cudaMalloc(&ctx->d_slots, S * ctx->ev_cap * sizeof(p25cu_event)));
@@ -277,6 +292,8 @@ extern "C" int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_d
     p.n_out = (unsigned)((ctx->a_abs + n) / D - p.m0);
     p.n_streams = (unsigned)S;
     p.ht = ctx->ht;
+    p.work_counter = ctx->d_work;
+    p.ticket_base = &ctx->ticket_base;
     // every stream's row must start 16-byte aligned: 2 cf32 or 8 u8 samples per 16-byte load
     p.aligned16 = ((n % (ctx->cfg.format == P25CU_FMT_U8_IQ ? 8 : 2)) == 0) && (((uintptr_t)d_in & 15) == 0);
     {
@@ -291,6 +308,8 @@ extern "C" int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_d
         p.n_seg = p.n_out ? (p.n_out + p.seg_out - 1) / p.seg_out : 1;
     }
     if (power_dbm) CK(cudaMemsetAsync(ctx->d_power, 0, S * sizeof(float), ctx->stream));
+    const bool timed = ctx->timing && n && ctx->n_timed < 128;
+    if (timed) CK(cudaEventRecord(ctx->tev[2 * ctx->n_timed], ctx->stream));
     if (n && ctx->n_captures) {
         // wideband capture -> 1,536 channels per capture (pfb.cu): spectra, per-channel baseband, carried state
         const size_t ch = p25cu_pfb_channels(), hist = p25cu_pfb_hist_rows();
@@ -311,6 +330,7 @@ extern "C" int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_d
         ctx->launches++;
         ctx->tail_cur ^= 1;
     }
+    if (timed) CK(cudaEventRecord(ctx->tev[2 * ctx->n_timed++ + 1], ctx->stream));
     CK(cudaEventRecord(ctx->ev_bb_ready[buf], ctx->stream));
     ctx->bb_last = buf;
     ctx->bb_cur = buf ^ 1;
@@ -373,7 +393,12 @@ extern "C" int p25cu_decode(p25cu_ctx* ctx, const float* baseband, size_t n) {
     w.ev_cap = ctx->ev_cap;
     w.stats = ctx->d_stats;
     w.tables = ctx->d_tables;
-    CK(p25cu_launch_walk(w, ws));
+    // Overlap mode: the walker of chunk k runs beside the demod kernel of chunk k + 1, whose persistent grid holds
+    // 3 CTAs x 320 threads x 56 allocated registers per SM.  Two 64-thread walker CTAs fit in the registers that are
+    // left (a third would keep a demod CTA from becoming resident: measured 0.51 vs 0.57 ms per step), so the walker
+    // is launched as a persistent grid of 2 CTAs per SM that walks the streams in several passes.
+    static const int persist = getenv("P25CU_WALK_PERSIST") ? atoi(getenv("P25CU_WALK_PERSIST")) : 2;
+    CK(p25cu_launch_walk(w, ws, ctx->overlap && persist ? (unsigned)(ctx->n_sm * persist) : 0u));
     CK(cudaEventRecord(ctx->ev_bb_free[buf], ws));
     if (!ctx->overlap) CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_bb_free[buf], 0));   // keep stream2 consumers ordered
     ctx->launches++;
@@ -506,6 +531,24 @@ extern "C" int p25cu_set_overlap(p25cu_ctx* ctx, int on) {
     return P25CU_OK;
 }
 extern "C" uint64_t p25cu_launch_count(const p25cu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int p25cu_demod_timing(p25cu_ctx* ctx, int enable, double* avg_ms, unsigned* count) {
+    if (!ctx) return P25CU_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double sum = 0.0;
+    for (unsigned i = 0; i < ctx->n_timed; i++) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->tev[2 * i], ctx->tev[2 * i + 1]));
+        sum += ms;
+    }
+    if (avg_ms) *avg_ms = ctx->n_timed ? sum / ctx->n_timed : 0.0;
+    if (count) *count = ctx->n_timed;
+    ctx->n_timed = 0;
+    if (enable && !ctx->tev[0])
+        for (int i = 0; i < 2 * 128; i++) CK(cudaEventCreate(&ctx->tev[i]));
+    ctx->timing = enable ? 1 : 0;
+    return P25CU_OK;
+}
 extern "C" int p25cu_device_baseband(p25cu_ctx* ctx, const float** ptr, size_t* row_stride, size_t* n_out) {
     if (!ctx || !ptr) return P25CU_ERR_ARG;
     *ptr = ctx->d_bb[ctx->bb_last] + P25CU_BB_HIST;

@@ -70,13 +70,15 @@ struct DdcParams {
     unsigned n_seg;               // segments per stream
     unsigned ht;                  // tail length in samples
     int aligned16;                // every chunk row starts 16-byte aligned and holds whole 16-byte groups
+    unsigned* work_counter;       // device ticket counter of the /50 kernel's dynamic work split (monotonic)
+    unsigned* ticket_base;        // host: tickets consumed by earlier launches
 };
 
 // kernels (defined in ddc_fm.cu / decode_walk.cu)
 cudaError_t p25cu_launch_ddc(const DdcParams& p, int format, int decimation, cudaStream_t st);
 cudaError_t p25cu_ddc_upload_taps();
 unsigned p25cu_ddc_tail_len(int decimation);
-cudaError_t p25cu_launch_walk(const WalkParams& p, cudaStream_t st);
+cudaError_t p25cu_launch_walk(const WalkParams& p, cudaStream_t st, unsigned max_blocks);
 cudaError_t p25cu_launch_compact(const WalkState* states, const p25cu_event* slots, unsigned ev_cap, unsigned n_streams,
                                  unsigned* offsets, p25cu_event* dense, cudaStream_t st);
 cudaError_t p25cu_launch_fec_selftest(const P25DevTables* tables, int kind, void* words, size_t count, int n, int k,

@@ -139,6 +139,12 @@ class Context:
     def set_overlap(self, on: bool):
         self._ck(self._L.p25cu_set_overlap(self._h, int(on)))
 
+    def demod_timing(self, enable: bool):
+        """(average demod-kernel ms, launches) recorded since the last call; sets whether recording continues."""
+        ms, n = C.c_double(0), C.c_uint(0)
+        self._ck(self._L.p25cu_demod_timing(self._h, int(enable), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     @property
     def cuda_stream(self) -> int:
         return int(self._L.p25cu_cuda_stream(self._h) or 0)
