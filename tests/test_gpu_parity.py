@@ -460,3 +460,43 @@ def test_demod_task_reports_power_every_fourth_chunk(p25, oracle):
             assert abs(pw[0] - pref) < 1e-2 and abs(pw[0] - (30 + 10 * np.log10(0.09))) < 1.0
     assert set(lens) == {3276, 3277} and sum(lens) == 9 * 16384 // 5      # phase carried across chunks
     ctx.close()
+
+
+# ------------------------------------------------------------------ error behaviour of the boundary (codes, never abort)
+def test_abi_error_codes_and_edge_sizes(p25, oracle):
+    ctx = p25.Context(2, fmt=p25.FMT_CF32_IQ, decimation=5, max_chunk_samples=4096, event_slots=4)
+    with pytest.raises(p25.P25Error) as e:                      # chunk larger than configured
+        ctx.demod(np.zeros((2, 5000), dtype=np.complex64), 5000)
+    assert e.value.status == -1 and "max_chunk_samples" in str(e.value)
+    with pytest.raises(p25.P25Error) as e:                      # decode(NULL) with nothing demodulated
+        ctx.decode()
+    assert e.value.status == -3
+    with pytest.raises(p25.P25Error) as e:
+        ctx.resync(7)                                           # no such stream
+    assert e.value.status == -1
+    # empty and tiny chunks are legal and keep the decimator phase
+    bb, n_out, _ = ctx.demod(np.zeros((2, 0), dtype=np.complex64), 0)
+    assert n_out == 0 and bb.shape == (2, 0)
+    total = 0
+    for m in (3, 1, 4, 2, 7):
+        bb, n_out, _ = ctx.demod(np.zeros((2, m), dtype=np.complex64), m)
+        total += n_out
+    assert total == 17 // 5
+    ctx.decode()
+    assert len(ctx.poll()) == 0
+    # more events than slots: the surplus is dropped and reported, the context stays usable
+    st = tx.control_channel(5, 6)
+    bb, _ = tx.baseband_48k(st.dibits, snr_db=20, seed=1)
+    ctx2 = p25.Context(1, max_chunk_samples=1024, max_baseband=len(bb), event_slots=4)
+    ctx2.decode(bb[None, :])
+    with pytest.raises(p25.P25Error) as e:
+        ctx2.poll()
+    assert e.value.status == -4
+    ctx2.decode(bb[None, :2000])
+    assert len(ctx2.poll()) <= 4
+    with pytest.raises(p25.P25Error):
+        p25.Context(1000, fmt=p25.FMT_CF32_IQ, decimation=400, max_chunk_samples=4000)   # not a multiple of 1536 channels
+    with pytest.raises(p25.P25Error):
+        p25.Context(4, decimation=7)
+    ctx.close()
+    ctx2.close()
