@@ -27,6 +27,7 @@ __constant__ float c_sync_fp[P25_FP_LEN];
 
 #define SEARCH_N 128                          // candidate positions per search step (4 per lane)
 #define WIN_LEN (P25_FP_LEN - 1 + SEARCH_N)  // samples needed to correlate them
+#define WIN_PAD 364                           // staged window, padded to whole 16-byte groups past the last LDS.128
 
 struct PendingEvent {
     unsigned kind, len, valid, pad;
@@ -36,7 +37,7 @@ struct PendingEvent {
 struct WalkShared {
     P25DevTables T;
     WalkState ws[P25CU_WALK_WARPS];
-    float win[P25CU_WALK_WARPS][WIN_LEN + 2];
+    alignas(16) float win[P25CU_WALK_WARPS][2 * WIN_PAD];    // the search window twice: [0, WIN_PAD) and shifted by one sample
     PendingEvent pend[P25CU_WALK_WARPS];
     alignas(16) unsigned char scr[P25CU_WALK_WARPS][192];   // decoder work area (syndromes, locator, IMBE results)
     unsigned short pn_a[116], pn_c[116];        // IMBE PN generator n steps ahead: p_n = pn_a[n] * p_0 + pn_c[n] (mod 2^16)
@@ -662,57 +663,108 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
     for (;;) {
         const int st = ws.state;
         if (st == WS_SYNC) {
-            // ---- frame-sync search over 128 positions: lane l owns positions pos + l + 32*h, h = 0..3
+            // ---- frame-sync search over 128 positions: lane l owns the four consecutive positions pos + 4 l + h.
+            // Position q correlates win[q .. q + 230]; a lane's four windows overlap in all but three samples, so the
+            // samples of four taps come from two 16-byte loads (the window is kept twice, the second copy shifted by
+            // one sample, which makes every packed operand an aligned register pair) and the second half of each
+            // load is reused by the next tap group: 2 LDS.128 per 16 FFMA2 instead of 16 LDS.32.  Each position's sum
+            // still runs over k = 0 .. 230 in order with one fmaf per tap, exactly like the oracle.
             const unsigned long long pos = ws.pos;
             if (pos >= end) break;
             const long long wbase = (long long)(pos - p0) + P25CU_BB_HIST - (P25_FP_LEN - 1);   // row index of win[0]
             const long long wlim = (long long)P25CU_BB_HIST + (long long)p.n;                   // first invalid row index
+            float* win1 = win + WIN_PAD;
             __syncwarp();
-            for (int i = lane; i < WIN_LEN; i += 32) win[i] = (wbase + i < wlim) ? __ldg(row + wbase + i) : 0.f;
+            for (int i = lane; i < WIN_PAD; i += 32) {
+                const float v = (i < WIN_LEN && wbase + i < wlim) ? __ldg(row + wbase + i) : 0.f;
+                win[i] = v;
+                if (i) win1[i - 1] = v;
+            }
             __syncwarp();
-            float2 cA = make_float2(0.f, 0.f), cB = cA, eA = cA, eB = cA;   // A: h = 0,1   B: h = 2,3
+            float2 c01 = make_float2(0.f, 0.f), c23 = c01, e01 = c01, e23 = c01;   // positions h = 0,1 | 2,3
             {
-                const float* w1 = win + lane;
-#pragma unroll 11
-                for (int k = 0; k < P25_FP_LEN; k++) {
-                    const float2 xa = make_float2(w1[k], w1[k + 32]), xb = make_float2(w1[k + 64], w1[k + 96]);
-                    const float2 f = make_float2(c_sync_fp[k], c_sync_fp[k]);
-                    cA = fma2(f, xa, cA);
-                    cB = fma2(f, xb, cB);
-                    eA = fma2(xa, xa, eA);
-                    eB = fma2(xb, xb, eB);
+                const float4* wa = reinterpret_cast<const float4*>(win) + lane;    // wa[m] = win[4 (lane + m) ..]
+                const float4* wb = reinterpret_cast<const float4*>(win1) + lane;   // wb[m] = win[4 (lane + m) + 1 ..]
+                float4 a = wa[0], b = wb[0];
+#pragma unroll 3
+                for (int m = 0; m < P25_FP_LEN / 4; m++) {                         // 57 full groups of 4 taps
+                    const float4 an = wa[m + 1], bn = wb[m + 1];
+                    const float f0 = c_sync_fp[4 * m], f1 = c_sync_fp[4 * m + 1], f2 = c_sync_fp[4 * m + 2], f3 = c_sync_fp[4 * m + 3];
+                    float2 x01 = make_float2(a.x, a.y), x23 = make_float2(a.z, a.w);          // tap 4m:     win[q + 4m]
+                    c01 = fma2(make_float2(f0, f0), x01, c01);
+                    c23 = fma2(make_float2(f0, f0), x23, c23);
+                    e01 = fma2(x01, x01, e01);
+                    e23 = fma2(x23, x23, e23);
+                    x01 = make_float2(b.x, b.y), x23 = make_float2(b.z, b.w);                 // tap 4m + 1
+                    c01 = fma2(make_float2(f1, f1), x01, c01);
+                    c23 = fma2(make_float2(f1, f1), x23, c23);
+                    e01 = fma2(x01, x01, e01);
+                    e23 = fma2(x23, x23, e23);
+                    x01 = make_float2(a.z, a.w), x23 = make_float2(an.x, an.y);               // tap 4m + 2
+                    c01 = fma2(make_float2(f2, f2), x01, c01);
+                    c23 = fma2(make_float2(f2, f2), x23, c23);
+                    e01 = fma2(x01, x01, e01);
+                    e23 = fma2(x23, x23, e23);
+                    x01 = make_float2(b.z, b.w), x23 = make_float2(bn.x, bn.y);               // tap 4m + 3
+                    c01 = fma2(make_float2(f3, f3), x01, c01);
+                    c23 = fma2(make_float2(f3, f3), x23, c23);
+                    e01 = fma2(x01, x01, e01);
+                    e23 = fma2(x23, x23, e23);
+                    a = an;
+                    b = bn;
+                }
+                {   // taps 228, 229, 230
+                    const float4 an = wa[P25_FP_LEN / 4 + 1];
+                    const float f0 = c_sync_fp[P25_FP_LEN - 3], f1 = c_sync_fp[P25_FP_LEN - 2], f2 = c_sync_fp[P25_FP_LEN - 1];
+                    float2 x01 = make_float2(a.x, a.y), x23 = make_float2(a.z, a.w);
+                    c01 = fma2(make_float2(f0, f0), x01, c01);
+                    c23 = fma2(make_float2(f0, f0), x23, c23);
+                    e01 = fma2(x01, x01, e01);
+                    e23 = fma2(x23, x23, e23);
+                    x01 = make_float2(b.x, b.y), x23 = make_float2(b.z, b.w);
+                    c01 = fma2(make_float2(f1, f1), x01, c01);
+                    c23 = fma2(make_float2(f1, f1), x23, c23);
+                    e01 = fma2(x01, x01, e01);
+                    e23 = fma2(x23, x23, e23);
+                    x01 = make_float2(a.z, a.w), x23 = make_float2(an.x, an.y);
+                    c01 = fma2(make_float2(f2, f2), x01, c01);
+                    c23 = fma2(make_float2(f2, f2), x23, c23);
+                    e01 = fma2(x01, x01, e01);
+                    e23 = fma2(x23, x23, e23);
                 }
             }
             const unsigned long long left = end - pos;
             const int nvalid = left < SEARCH_N ? (int)left : SEARCH_N;
-            const float corr[4] = {cA.x, cA.y, cB.x, cB.y}, en[4] = {eA.x, eA.y, eB.x, eB.y};
-            int fire_off = -1;
-            float pcn = ws.prev_corr;      // predecessor of lane 0 in the current quarter
-            int pan = ws.prev_above, hpn = ws.have_prev;
-            float lc = 0.f;
-            int la = 0;
+            const float corr[4] = {c01.x, c01.y, c23.x, c23.y}, en[4] = {e01.x, e01.y, e23.x, e23.y};
+            bool ab[4];
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+                ab[h] = 4 * lane + h < nvalid && corr[h] > 0.f && (corr[h] * corr[h] >= P25_SYNC_RHO2_EFP * en[h]);
+            // the detector fires on the first position that is above threshold, whose predecessor was above too, and
+            // whose correlation did not grow; the predecessor of a lane's first position is the lane below's last one
+            float pc = __shfl_up_sync(FULL, corr[3], 1);
+            int pa = __shfl_up_sync(FULL, (int)ab[3], 1), hp = 1;
+            if (lane == 0) {
+                pc = ws.prev_corr;
+                pa = ws.prev_above;
+                hp = ws.have_prev;
+            }
+            unsigned cand = 0xFFFFFFFFu;
 #pragma unroll
             for (int h = 0; h < 4; h++) {
-                const bool v = lane + 32 * h < nvalid;
-                const bool ab = v && corr[h] > 0.f && (corr[h] * corr[h] >= P25_SYNC_RHO2_EFP * en[h]);
-                float pc = __shfl_up_sync(FULL, corr[h], 1);
-                int pa = __shfl_up_sync(FULL, (int)ab, 1), hp = 1;
-                if (lane == 0) {
-                    pc = pcn;
-                    pa = pan;
-                    hp = hpn;
-                }
-                const unsigned fm = __ballot_sync(FULL, v && hp && ab && pa && corr[h] <= pc);
-                if (fm && fire_off < 0) fire_off = 32 * h + __ffs(fm) - 1;
-                // hand the last position of this quarter to lane 0 of the next one
-                pcn = __shfl_sync(FULL, corr[h], 31);
-                pan = __shfl_sync(FULL, (int)ab, 31);
-                hpn = 1;
-                if (nvalid - 1 >= 32 * h && nvalid - 1 < 32 * h + 32) {
-                    lc = __shfl_sync(FULL, corr[h], (nvalid - 1) & 31);
-                    la = __shfl_sync(FULL, (int)ab, (nvalid - 1) & 31);
-                }
+                if (cand == 0xFFFFFFFFu && hp && ab[h] && pa && corr[h] <= pc) cand = 4 * lane + h;
+                pc = corr[h];
+                pa = (int)ab[h];
+                hp = 1;
             }
+            const unsigned first = __reduce_min_sync(FULL, cand);
+            const int fire_off = first == 0xFFFFFFFFu ? -1 : (int)first;
+            // state handed to the next step: the last valid position of this one
+            const int ql = nvalid - 1, hl = ql & 3;
+            const float csel = hl == 0 ? corr[0] : hl == 1 ? corr[1] : hl == 2 ? corr[2] : corr[3];
+            const int asel = (int)(hl == 0 ? ab[0] : hl == 1 ? ab[1] : hl == 2 ? ab[2] : ab[3]);
+            const float lc = __shfl_sync(FULL, csel, ql >> 2);
+            const int la = __shfl_sync(FULL, asel, ql >> 2);
             if (fire_off < 0) {
                 __syncwarp();
                 if (lane == 0) {
