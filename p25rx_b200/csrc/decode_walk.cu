@@ -54,6 +54,8 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2*>(&r);
 }
 static_assert(sizeof(P25DevTables) % 16 == 0, "tables are staged with 16-byte copies");
+// pull the cache lines the next step will read into L1 (the row stays in L2 after the demod kernel wrote it)
+__device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 struct WarpCtx {
     const WalkParams* p;
@@ -680,6 +682,7 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
                 win[i] = v;
                 if (i) win1[i - 1] = v;
             }
+            if (lane < 5 && wbase + WIN_LEN + 32 * lane < wlim) prefetch_l1(row + wbase + WIN_LEN + 32 * lane);   // next step's new samples
             __syncwarp();
             float2 c01 = make_float2(0.f, 0.f), c23 = c01, e01 = c01, e23 = c01;   // positions h = 0,1 | 2,3
             {
@@ -834,6 +837,10 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
         const bool stb = ((fpos0 + 32 + lane) % P25_STATUS_PERIOD) == P25_STATUS_PERIOD - 1;
         const float* sp = row + (long long)(t0 - p0) + P25CU_BB_HIST + P25_SPS * lane;
         const float sa = va ? __ldg(sp) : 0.f, sb = vb ? __ldg(sp + 32 * P25_SPS) : 0.f;
+        {   // the 64 symbol instants of the next step span 640 samples = 20 cache lines
+            const long long nx = (long long)(t0 - p0) + P25CU_BB_HIST + 64 * P25_SPS + 32 * lane;
+            if (lane < 21 && nx < (long long)P25CU_BB_HIST + (long long)p.n) prefetch_l1(row + nx);
+        }
         const float pth = ws.pth, mid = ws.mid, nth = ws.nth;
         const int da = sa > pth ? 1 : (sa > mid ? 0 : (sa > nth ? 2 : 3));   // [STD] 01 +3, 00 +1, 10 -1, 11 -3
         const int db = sb > pth ? 1 : (sb > mid ? 0 : (sb > nth ? 2 : 3));
