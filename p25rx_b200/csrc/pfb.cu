@@ -16,10 +16,10 @@
 //   v_m[r] = sum_{p<4} h[r + 1536 p] x[n_m - r - 1536 p]           (4 complex-by-real taps per branch)
 //   y_k[m] = sum_q v_m[(q + n_m) mod 1536] exp(+2j pi k q / 1536)   (one 1,536-point inverse DFT per output time)
 //
-// Kernel A (p25_pfb_kernel): a CTA stages the input window of 8 consecutive output times in shared memory
-// (6,144 + 7 * 400 samples, so every input sample is fetched about 2.8 times, from L2), forms the branches and
-// runs the DFT as a mixed-radix Stockham FFT 3 x 8 x 8 x 8 in shared memory (radix-8 butterflies in registers,
-// twiddles from a 1,536-entry table); the last pass writes the spectrum time-major, Y[m][k], fully coalesced.
+// Kernel A (p25_pfb_kernel): a CTA owns a run of consecutive output times; for each it forms the branches from the
+// input window in global memory (consecutive windows overlap by 93 %: L1/L2 hits) and runs the DFT as a mixed-radix
+// Stockham FFT 3 x 8 x 8 x 8 in shared memory (radix-8 butterflies in registers, twiddles from a 1,536-entry table);
+// the last pass writes the spectrum time-major, Y[m][k], fully coalesced.
 // Kernel B (p25_chan_fm_kernel): a CTA takes 32 channels x 128 output times of Y (256-byte row segments, lanes =
 // channels), runs the channel filter as a sliding register window down each lane's column, the discriminator
 // and the boxcar, and transposes through shared memory so that every channel's baseband row is written in
@@ -30,13 +30,14 @@
 namespace pfb {
 
 constexpr int N = P25_PFB_N, M = P25_PFB_M, P = P25_PFB_P, L = N * P;
-constexpr int TM = 8;                      // output times per CTA (kernel A)
 constexpr int NT = 256;
-constexpr int WLEN = L + M * (TM - 1);     // staged input window
 static_assert(N == 3 * 8 * 8 * 8, "FFT plan is 3 x 8 x 8 x 8");
 
+// Shared memory holds only the FFT ping-pong buffers and the twiddles (37 KB -> 6 CTAs per SM).  The input window
+// (6,144 samples per output time, 93 % of it shared with the previous output time of the same CTA) is read straight
+// from global memory: the re-reads hit L1/L2, and the occupancy this buys matters more than the staging it saves
+// (staged window: 2 CTAs per SM, 23 % issue utilisation).
 struct SmemA {
-    float2 xw[WLEN];
     float2 fa[N], fb[N];
     float2 tw[N];
 };
@@ -105,41 +106,43 @@ struct PfbParams {
     unsigned y_rows, hist;
 };
 
-__global__ void __launch_bounds__(NT) p25_pfb_kernel(const PfbParams p) {
+__global__ void __launch_bounds__(NT) p25_pfb_kernel(const PfbParams p, const unsigned times_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemA& sm = *reinterpret_cast<SmemA*>(smem_raw);
     const int tid = threadIdx.x;
     const unsigned cap = blockIdx.y;
-    const unsigned t_first = blockIdx.x * TM;                    // first output time of this CTA, relative to m0
+    const unsigned t_first = blockIdx.x * times_per_cta;         // this CTA's consecutive output times, relative to m0
+    const unsigned t_last = min(t_first + times_per_cta, p.n_out);
     const float2* chunk = p.iq + (size_t)cap * p.n;
     const float2* tail = p.tail_in + (size_t)cap * L;
-    // newest input of output m (absolute) is n_m = M m + M - 1; window = [n_first - (L - 1), n_first + M (TM - 1)]
-    const long long n_first = (long long)M * ((long long)p.m0 + t_first) + (M - 1);
-    const long long w0 = n_first - (L - 1) - (long long)p.a0 + L;   // logical index (tail ++ chunk) of xw[0]; tail holds L samples
     for (int i = tid; i < N; i += NT) sm.tw[i] = p.twiddle[i];
-    for (int i = tid; i < WLEN; i += NT) {
-        const long long l = w0 + i;
-        float2 v = make_float2(0.f, 0.f);
-        if (l >= 0 && l < L) v = tail[l];
-        else if (l >= L && l - L < (long long)p.n) v = __ldg(chunk + (l - L));
-        sm.xw[i] = v;
-    }
-    __syncthreads();
     float2* yc = p.y + ((size_t)cap * p.y_rows + p.hist) * N;
+    __syncthreads();
 
-    for (int t = 0; t < TM; t++) {
-        const unsigned tr = t_first + t;
-        if (tr >= p.n_out) break;                                // uniform
-        const int e = (L - 1) + M * t;                           // xw index of the newest input of this output time
-        const int nm_mod = (int)(((unsigned long long)(n_first + (long long)M * t)) % N);
+    for (unsigned tr = t_first; tr < t_last; tr++) {
+        // newest input of output m (absolute) is n_m = M m + M - 1; its logical index in (tail ++ chunk) is e
+        const long long n_m = (long long)M * ((long long)p.m0 + tr) + (M - 1);
+        const long long e = n_m - (long long)p.a0 + L;           // tail holds L samples
+        const int nm_mod = (int)((unsigned long long)n_m % N);
+        const bool in_chunk = e - (L - 1) >= L;                  // the whole window lies in this chunk
         // branches: v[r] = sum_p h[r + N p] * x[n_m - r - N p], stored at q = (r - n_m) mod N
 #pragma unroll
         for (int jr = 0; jr < N / NT; jr++) {
             const int r = tid + jr * NT;
             float2 acc = make_float2(0.f, 0.f);
+            if (in_chunk) {
+                const float2* x = chunk + (e - L - r);
 #pragma unroll
-            for (int pp = 0; pp < P; pp++) {
-                acc = cfma(__ldg(p.taps + r + N * pp), sm.xw[e - r - N * pp], acc);
+                for (int pp = 0; pp < P; pp++) acc = cfma(__ldg(p.taps + r + N * pp), __ldg(x - N * pp), acc);
+            } else {
+#pragma unroll
+                for (int pp = 0; pp < P; pp++) {
+                    const long long l = e - r - N * pp;
+                    float2 xv = make_float2(0.f, 0.f);
+                    if (l >= L) xv = __ldg(chunk + (l - L));
+                    else if (l >= 0) xv = tail[l];
+                    acc = cfma(__ldg(p.taps + r + N * pp), xv, acc);
+                }
             }
             int q = r - nm_mod;
             if (q < 0) q += N;
@@ -163,9 +166,7 @@ __global__ void __launch_bounds__(NT) p25_pfb_kernel(const PfbParams p) {
         if (tid < N / 8) pass8<24, false>(sm.fa, sm.fb, sm.tw, tid);
         __syncthreads();
         if (tid < N / 8) pass8<192, true>(sm.fb, yc + (size_t)tr * N, sm.tw, tid);   // natural order, straight to HBM
-        // fa is rewritten only after the next iteration's first barrier-free phase reads xw: fb readers are done at the
-        // barrier below
-        __syncthreads();
+        __syncthreads();                                         // fb is read until here; fa is rewritten next
     }
 }
 
@@ -337,8 +338,21 @@ cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out
         a.n_captures = n_captures;
         a.y_rows = y_rows;
         a.hist = hist;
-        const dim3 ga((n_out + pfb::TM - 1) / pfb::TM, n_captures);
-        pfb::p25_pfb_kernel<<<ga, pfb::NT, sizeof(pfb::SmemA), st>>>(a);
+        // one wave of CTAs: consecutive output times per CTA (their windows overlap, so re-reads hit L1), as many CTAs
+        // as fit at once
+        static int slots = 0;
+        if (!slots) {
+            int dev = 0, n_sm = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pfb::p25_pfb_kernel, pfb::NT, sizeof(pfb::SmemA));
+            slots = n_sm * (per_sm > 0 ? per_sm : 1);
+        }
+        unsigned per_cap = (unsigned)slots / n_captures;
+        if (per_cap < 1) per_cap = 1;
+        const unsigned tpc = (n_out + per_cap - 1) / per_cap;            // output times per CTA
+        const dim3 ga((n_out + tpc - 1) / tpc, n_captures);
+        pfb::p25_pfb_kernel<<<ga, pfb::NT, sizeof(pfb::SmemA), st>>>(a, tpc);
         pfb::ChanParams b;
         b.y = y;
         b.bb = bb;
