@@ -927,16 +927,22 @@ constexpr int R = 4;                        // outputs per lane
 constexpr int NOUT = 31 * R;                // 124 outputs per warp iteration
 constexpr int XNEW = 5 * NOUT;              // 620 fresh input samples per iteration
 constexpr int XN = 32 * 5 * R;              // 640 samples read (the ghost lane's 20 included)
-constexpr int AL = 8, ES = 2;
-constexpr int XLEN = (XN + 2 * AL - 2) / AL * AL;     // 648
-constexpr int XBYTES = (XLEN * ES + 127) / 128 * 128; // 1408
 constexpr int WARPS = 4;                    // per CTA
+template <int FMT>
+struct Fmt {                                // u8: 1.4 KB slices, 5 CTAs/SM; cf32: 5.1 KB slices, 4 CTAs/SM
+    static constexpr bool U8 = FMT == P25CU_FMT_U8_IQ;
+    static constexpr int AL = U8 ? 8 : 2, ES = U8 ? 2 : 8;
+    static constexpr int XLEN = (XN + 2 * AL - 2) / AL * AL;
+    static constexpr int XBYTES = (XLEN * ES + 127) / 128 * 128;
+    static constexpr int MINB = U8 ? 5 : 4;
+};
 constexpr int HROWS = (P25_TAPS_CHAN - 1) / R;        // 10 history rows of the decimator output
 constexpr int DROWS = 3;                    // history rows of the discriminator output (>= 9 samples)
 static_assert((P25_TAPS_CHAN - 1) % R == 0 && DROWS * R >= P25_BOXCAR - 1, "history rows");
 
+template <int FMT>
 struct __align__(128) WarpSm {
-    unsigned char xs[2][XBYTES];
+    unsigned char xs[2][Fmt<FMT>::XBYTES];
     float4 ydA[HROWS + 32], ydB[HROWS + 32];    // row i: (yd[4i], yd[4i+1]) | (yd[4i+2], yd[4i+3])
     float4 d4[DROWS + 32];
     unsigned long long full[2];
@@ -944,8 +950,10 @@ struct __align__(128) WarpSm {
 
 // bulk copy of the slice whose first input has logical index l0 (tail ++ chunk); 32-bit index arithmetic, the slice
 // that still overlaps the carried tail (first iterations of a chunk only) takes the two-copy path
-__device__ __forceinline__ void issue_slice(WarpSm& sm, int stage, int ht, int lend, const unsigned char* tail,
+template <int FMT>
+__device__ __forceinline__ void issue_slice(WarpSm<FMT>& sm, int stage, int ht, int lend, const unsigned char* tail,
                                             const unsigned char* chunk, int l0) {
+    constexpr int AL = Fmt<FMT>::AL, ES = Fmt<FMT>::ES, XLEN = Fmt<FMT>::XLEN;
     const int la = l0 & ~(AL - 1);
     const int lb = min(la + XLEN, lend);
     if (la >= ht) {
@@ -961,14 +969,13 @@ __device__ __forceinline__ void issue_slice(WarpSm& sm, int stage, int ht, int l
     if (nc) tma_load_1d(&sm.xs[stage][nt * ES], chunk, nc * ES, &sm.full[stage]);
 }
 
-#ifndef W5_MINB
-#define W5_MINB 5
-#endif
-__global__ void __launch_bounds__(32 * WARPS, W5_MINB) p25_ddc5_warp_kernel(const DdcParams p, const unsigned its_per_stream,
-                                                                      const float dc, const float pw_scale) {
+template <int FMT>
+__global__ void __launch_bounds__(32 * WARPS, Fmt<FMT>::MINB) p25_ddc5_warp_kernel(const DdcParams p, const unsigned its_per_stream,
+                                                                             const float dc, const float pw_scale) {
+    constexpr int AL = Fmt<FMT>::AL, ES = Fmt<FMT>::ES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSm& sm = reinterpret_cast<WarpSm*>(smem_raw)[warp];
+    WarpSm<FMT>& sm = reinterpret_cast<WarpSm<FMT>*>(smem_raw)[warp];
     if (lane == 0) {
         mbar_init(&sm.full[0], 1);
         mbar_init(&sm.full[1], 1);
@@ -995,8 +1002,8 @@ __global__ void __launch_bounds__(32 * WARPS, W5_MINB) p25_ddc5_warp_kernel(cons
     const unsigned char* chunk = (const unsigned char*)p.iq + s * row_bytes;
     const unsigned char* tail = (const unsigned char*)p.tail_in + s * tail_bytes;
     if (lane == 0) {                                        // warm-up and first stored iteration of the first piece
-        issue_slice(sm, 0, ht, lend, tail, chunk, l_base + XNEW * (it_first - 1));
-        issue_slice(sm, 1, ht, lend, tail, chunk, l_base + XNEW * it_first);
+        issue_slice<FMT>(sm, 0, ht, lend, tail, chunk, l_base + XNEW * (it_first - 1));
+        issue_slice<FMT>(sm, 1, ht, lend, tail, chunk, l_base + XNEW * it_first);
     }
     float2 c_carry = make_float2(0.f, 0.f);
     unsigned use = 0;
@@ -1019,9 +1026,29 @@ __global__ void __launch_bounds__(32 * WARPS, W5_MINB) p25_ddc5_warp_kernel(cons
         {
             float2 x[5 * R];
             const int s0 = skew + 5 * R * lane;
-            const unsigned* wp = reinterpret_cast<const unsigned*>(sm.xs[stage]) + (s0 >> 1);
-            if (s0 & 1) load_u8<R, true>(wp, x);
-            else load_u8<R, false>(wp, x);
+            if constexpr (Fmt<FMT>::U8) {
+                const unsigned* wp = reinterpret_cast<const unsigned*>(sm.xs[stage]) + (s0 >> 1);
+                if (s0 & 1) load_u8<R, true>(wp, x);
+                else load_u8<R, false>(wp, x);
+            } else {
+                // 16-byte loads (two samples): half the wavefronts of LDS.64 at this 160-byte lane stride
+                const float4* xp = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(sm.xs[stage]) + (s0 & ~1));
+                if (s0 & 1) {
+#pragma unroll
+                    for (int i = 0; i <= 5 * R / 2; i++) {
+                        const float4 v = xp[i];
+                        if (i > 0) x[2 * i - 1] = make_float2(v.x, v.y);
+                        if (i < 5 * R / 2) x[2 * i] = make_float2(v.z, v.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 5 * R / 2; i++) {
+                        const float4 v = xp[i];
+                        x[2 * i] = make_float2(v.x, v.y);
+                        x[2 * i + 1] = make_float2(v.z, v.w);
+                    }
+                }
+            }
             float2 lft[R];
 #pragma unroll
             for (int r = 0; r < R; r++) {
@@ -1046,8 +1073,8 @@ __global__ void __launch_bounds__(32 * WARPS, W5_MINB) p25_ddc5_warp_kernel(cons
         sm.ydB[HROWS + lane] = make_float4(own[2].x, own[2].y, own[3].x, own[3].y);
         __syncwarp();                                                                 // S1: xs[stage] consumed, rows visible
         if (lane == 0) {                                    // prefetch two iterations ahead (possibly into the next piece)
-            if (j + 2 < npiece) issue_slice(sm, stage, ht, lend, tail, chunk, l_base + XNEW * (it + 2));
-            else if (left) issue_slice(sm, stage, ht, lend, tail + tail_bytes, chunk + row_bytes, l_base + XNEW * (j + 1 - npiece));
+            if (j + 2 < npiece) issue_slice<FMT>(sm, stage, ht, lend, tail, chunk, l_base + XNEW * (it + 2));
+            else if (left) issue_slice<FMT>(sm, stage, ht, lend, tail + tail_bytes, chunk + row_bytes, l_base + XNEW * (j + 1 - npiece));
         }
 
         // ---- channel-select FIR: outputs 4 lane + r, window = rows lane .. lane + 10 (44 samples, s = 40 + r - k)
@@ -1220,10 +1247,11 @@ static cudaError_t launch_fast5(const DdcParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+template <int FMT>
 static cudaError_t launch_w5(const DdcParams& p, cudaStream_t st) {
     static int grid_cache = 0;
-    auto kern = w5::p25_ddc5_warp_kernel;
-    const size_t smem = sizeof(w5::WarpSm) * w5::WARPS;
+    auto kern = w5::p25_ddc5_warp_kernel<FMT>;
+    const size_t smem = sizeof(w5::WarpSm<FMT>) * w5::WARPS;
     if (!grid_cache) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1242,17 +1270,23 @@ static cudaError_t launch_w5(const DdcParams& p, cudaStream_t st) {
     double gd = 0.0, gc = 0.0;
     for (int k = 0; k < P25_TAPS_DECIM; k++) gd += (double)P25_TAPS_DECIM_H[k];
     for (int k = 0; k < P25_TAPS_CHAN; k++) gc += (double)P25_TAPS_CHAN_H[k];
-    kern<<<grid, 32 * w5::WARPS, smem, st>>>(p, ips, (float)(0.5 * gd * gc), (float)(1.0 / (127.5 * 127.5)));
+    const bool u8 = FMT == P25CU_FMT_U8_IQ;
+    kern<<<grid, 32 * w5::WARPS, smem, st>>>(p, ips, u8 ? (float)(0.5 * gd * gc) : 0.f, u8 ? (float)(1.0 / (127.5 * 127.5)) : 1.f);
     return cudaGetLastError();
 }
 
-int p25cu_ddc5_variant = 1;   // 1: warp-autonomous kernel for u8 (default), 0: tile kernel (kept for cf32 and for A/B timing)
+// /5 fast paths: bit 0 = warp-autonomous kernel for u8, bit 1 = for cf32 (otherwise the tile kernel); A/B switch P25CU_DDC5
+static int ddc5_variant() {
+    static const int v = getenv("P25CU_DDC5") ? atoi(getenv("P25CU_DDC5")) : 3;
+    return v;
+}
 
 cudaError_t p25cu_launch_ddc(const DdcParams& p, int format, int decimation, cudaStream_t st) {
     if (p.n_out == 0 && p.n == 0) return cudaSuccess;
-    if (decimation == 5 && format == P25CU_FMT_U8_IQ && p25cu_ddc5_variant == 1 && p.aligned16 && p.n_out > 0 && p.a0 >= p.ht &&
-        p.n >= p.ht && p.ht == (unsigned)Cfg<false>::HT)
-        return launch_w5(p, st);
+    if (decimation == 5 && p.aligned16 && p.n_out > 0 && p.a0 >= p.ht && p.n >= p.ht && p.ht == (unsigned)Cfg<false>::HT) {
+        if (format == P25CU_FMT_U8_IQ && (ddc5_variant() & 1)) return launch_w5<P25CU_FMT_U8_IQ>(p, st);
+        if (format == P25CU_FMT_CF32_IQ && (ddc5_variant() & 2)) return launch_w5<P25CU_FMT_CF32_IQ>(p, st);
+    }
     // /5 fast path: aligned rows, the whole history inside the stream (no implicit zeros), chunk at least one tail long
     if (decimation == 5 && p.aligned16 && p.n_out > 0 && p.a0 >= p.ht && p.n >= p.ht && p.ht == (unsigned)Cfg<false>::HT)
         return format == P25CU_FMT_CF32_IQ ? launch_fast5<P25CU_FMT_CF32_IQ>(p, st) : launch_fast5<P25CU_FMT_U8_IQ>(p, st);
