@@ -310,8 +310,10 @@ __device__ __noinline__ int bm_runtime(const P25DevTables& T, const unsigned cha
     lam[0] = 1;
     B[0] = 1;
     int L = 0, m = 1, b = 1;
+#pragma unroll 1
     for (int r = 0; r < N; r++) {
         int d = S[r];
+#pragma unroll 1
         for (int i = 1; i <= L; i++) d ^= p25_gf_mul(T, lam[i], S[r - i]);
         if (d == 0) {
             m++;
@@ -319,13 +321,17 @@ __device__ __noinline__ int bm_runtime(const P25DevTables& T, const unsigned cha
         }
         const int coef = p25_gf_div(T, d, b);
         if (2 * L <= r) {
+#pragma unroll 1
             for (int i = 0; i <= N; i++) Tm[i] = lam[i];
+#pragma unroll 1
             for (int i = 0; i + m <= N; i++) lam[i + m] ^= (unsigned char)p25_gf_mul(T, coef, B[i]);
             L = r + 1 - L;
+#pragma unroll 1
             for (int i = 0; i <= N; i++) B[i] = Tm[i];
             b = d;
             m = 1;
         } else {
+#pragma unroll 1
             for (int i = 0; i + m <= N; i++) lam[i + m] ^= (unsigned char)p25_gf_mul(T, coef, B[i]);
             m++;
         }
@@ -337,6 +343,7 @@ __device__ __forceinline__ int warp_rs_syndromes(const P25DevTables& T, const un
     int acc = 0;
     if (lane < nroots) {
         const int a = T.gf_exp[lane + 1];
+#pragma unroll 1
         for (int i = 0; i < n; i++) acc = p25_gf_mul(T, acc, a) ^ sym[i];
     }
     return acc;
@@ -361,6 +368,7 @@ __device__ __noinline__ int warp_rs_decode(const P25DevTables& T, unsigned char*
     __syncwarp();
     if (lane < nroots) {
         int acc = 0;
+#pragma unroll 1
         for (int j = 0; j <= lane && j <= L; j++) acc ^= p25_gf_mul(T, lam[j], S[lane - j]);
         omega[lane] = (unsigned char)acc;
     }

@@ -18,9 +18,13 @@
 #ifdef P25_FEC_HOSTCHECK
 #define P25_FN static inline
 #define P25_POPC(x) __builtin_popcount(x)
+#define P25_ROLLED
 #else
 #define P25_FN __device__ __forceinline__
 #define P25_POPC(x) __popc(x)
+// The walker is instruction-fetch bound on voice traffic (stall_no_inst 42 %: ~150 KB of code, every warp in a different
+// decoder); the short bit loops below stay rolled so that the decoders fit the instruction cache.
+#define P25_ROLLED _Pragma("unroll 1")
 #endif
 
 // Device-resident copy of the decode tables (filled from p25_tables.h at context creation;
@@ -116,6 +120,7 @@ P25_FN int p25_berlekamp_massey(const P25DevTables& T, const uint8_t* S, uint8_t
 
 P25_FN int p25_poly_eval(const P25DevTables& T, const uint8_t* p, int deg, int x) {
     int acc = 0;
+    P25_ROLLED
     for (int i = deg; i >= 0; i--) acc = p25_gf_mul(T, acc, x) ^ p[i];
     return acc;
 }
@@ -169,6 +174,7 @@ P25_FN int p25_bch_decode(const P25DevTables& T, uint64_t word63, uint32_t* data
 
 // ------------------------------------------------------------------ Golay / Hamming / cyclic
 P25_FN uint32_t p25_polymod(uint32_t a, uint32_t g, int gdeg, int abits) {
+    P25_ROLLED
     for (int i = abits - 1; i >= gdeg; i--)
         if ((a >> i) & 1) a ^= g << (i - gdeg);
     return a;
@@ -206,6 +212,7 @@ P25_FN int p25_golay18_decode(const P25DevTables& T, uint32_t word, uint32_t* da
 P25_FN int p25_hamming15_decode(const P25DevTables& T, uint32_t word, uint32_t* data11) {
     word &= 0x7FFF;
     uint32_t p = 0;
+    P25_ROLLED
     for (int i = 0; i < 11; i++)
         if ((word >> (14 - i)) & 1) p ^= T.ham15_cols[i];
     const uint32_t s = p ^ (word & 0xF);
@@ -217,6 +224,7 @@ P25_FN int p25_hamming15_decode(const P25DevTables& T, uint32_t word, uint32_t* 
 P25_FN int p25_hamming10_decode(const P25DevTables& T, uint32_t word, uint32_t* data6) {
     word &= 0x3FF;
     uint32_t p = 0;
+    P25_ROLLED
     for (int i = 0; i < 6; i++)
         if ((word >> (9 - i)) & 1) p ^= T.ham10_cols[i];
     const uint32_t s = p ^ (word & 0xF);
@@ -366,6 +374,7 @@ P25_FN void p25_imbe_decode(const P25DevTables& T, const uint8_t* dibits, uint32
 // ------------------------------------------------------------------ bit packing helpers
 P25_FN uint32_t p25_take_bits(const uint8_t* dibits, int bit0, int nbits) {
     uint32_t v = 0;
+    P25_ROLLED
     for (int i = 0; i < nbits; i++) {
         const int b = bit0 + i;
         v = (v << 1) | ((dibits[b >> 1] >> (1 - (b & 1))) & 1u);
