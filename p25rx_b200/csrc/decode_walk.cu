@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
                 const float4* wa = reinterpret_cast<const float4*>(win) + lane;    // wa[m] = win[4 (lane + m) ..]
                 const float4* wb = reinterpret_cast<const float4*>(win1) + lane;   // wb[m] = win[4 (lane + m) + 1 ..]
                 float4 a = wa[0], b = wb[0];
-#pragma unroll 3
+#pragma unroll 2
                 for (int m = 0; m < P25_FP_LEN / 4; m++) {                         // 57 full groups of 4 taps
                     const float4 an = wa[m + 1], bn = wb[m + 1];
                     const float f0 = c_sync_fp[4 * m], f1 = c_sync_fp[4 * m + 1], f2 = c_sync_fp[4 * m + 2], f3 = c_sync_fp[4 * m + 3];
