@@ -30,6 +30,23 @@ def main():
                         events=ev.view(np.uint8))
     print(len(ev), "events")
 
+    # demod fixture: the reference-native shape (u8 IQ at 240 kS/s, src/demod.rs:70-117) -> 48 kHz baseband + power
+    st = tx.control_channel(950, 3, lead_idle=10)
+    iq = tx.iq_to_u8(tx.modulate_iq(st.dibits, 240_000, snr_db=25, cfo_hz=120.0, seed=5, amplitude=0.35))[: 2 * 40_000]
+    chain = po.DemodChain(po.FMT_U8, False)
+    parts = [chain.feed(iq[2 * a: 2 * b], want_power=True) for a, b in ((0, 16384), (16384, 32768), (32768, 40_000))]
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), "demod_golden.npz"), iq_u8=iq,
+                        baseband=np.concatenate([p[0] for p in parts]), power_dbm=np.array([p[1] for p in parts], dtype=np.float32))
+
+    # channelizer fixture: 19.2 MS/s capture -> channel spectra (oracle/pfb_oracle.py), the last 8 output times of 96 channels
+    from oracle import pfb_oracle as pfb
+    st = tx.control_channel(951, 1, lead_idle=0)
+    cap = tx.wideband_capture({5: (st.dibits, 0.05, 0.0), 1530: (st.dibits[::-1].copy(), 0.03, 50.0)}, 12_000, noise_db=-50.0, seed=9)
+    y = pfb.channelize(cap)
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), "pfb_golden.npz"), capture=cap, rows=np.arange(22, 30),
+                        channels=np.arange(0, 1536, 16) + 5 % 16, spectra=y[22:30][:, (np.arange(0, 1536, 16) + 5 % 16)].astype(np.complex64))
+    print("demod", sum(len(p[0]) for p in parts), "baseband samples; pfb", y.shape)
+
 
 if __name__ == "__main__":
     main()

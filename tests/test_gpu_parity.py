@@ -273,6 +273,26 @@ def test_golden_fixtures(p25):
     ev = p25.MessageReceiver(ctx).feed(bb)
     assert events_key(ev) == events_key(exp.view(p25.EVENT_DTYPE).reshape(-1))
     ctx.close()
+    # demod fixture: u8 IQ in the reference's chunking -> baseband and power (generic kernel, then the /5 fast kernel)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "demod_golden.npz"))
+    iq, exp, pw = g["iq_u8"], g["baseband"], g["power_dbm"]
+    ctx = p25.Context(1, fmt=p25.FMT_U8_IQ, decimation=5, max_chunk_samples=16384)
+    got, gpw = [], []
+    for a, b in ((0, 16384), (16384, 32768), (32768, 40_000)):
+        bb, _, p = ctx.demod(np.ascontiguousarray(iq[None, 2 * a: 2 * b]), b - a, want_power=True)
+        got.append(bb[0])
+        gpw.append(p[0])
+    assert np.max(np.abs(np.concatenate(got) - exp)) < BB_TOL and np.max(np.abs(np.array(gpw) - pw)) < 1e-2
+    ctx.close()
+    # channelizer fixture: capture -> spectra of the last 8 output times, 96 channels
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pfb_golden.npz"))
+    cap = g["capture"]
+    ctx = p25.Context(1536, fmt=p25.FMT_CF32_IQ, decimation=400, max_chunk_samples=len(cap))
+    ctx.demod(np.ascontiguousarray(cap[None, :]), len(cap), want_baseband=False)
+    y = ctx.channelizer_output()[0]
+    got = y[g["rows"]][:, g["channels"]]
+    assert np.max(np.abs(got - g["spectra"])) < 2e-5 * np.max(np.abs(g["spectra"]))
+    ctx.close()
 
 
 def test_full_size_properties(p25):
