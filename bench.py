@@ -210,6 +210,23 @@ def pin_to_gpu_numa_node(index: int) -> None:
         pass
 
 
+def single_stream_split(po, native: bool, fmt: int, front: bool, row: np.ndarray, decim: int) -> dict:
+    """The reference's actual shape: one stream on one thread, timed separately for the `demod` thread's
+    work (src/demod.rs:62-119) and the `receiver` thread's (src/recv.rs:140-167), a few repetitions of one step's row."""
+    reps = 4
+    chain, rx = po.DemodChain(fmt, front, native=native), po.MessageReceiver(native=native)
+    t0 = time.perf_counter()
+    bbs = [chain.feed(row) for _ in range(reps)]
+    t1 = time.perf_counter()
+    for bb in bbs:
+        rx.feed(bb)
+    t2 = time.perf_counter()
+    n_in = reps * (row.size // (2 if fmt == po.FMT_U8 else 1))
+    return {"threads": 1, "demod_iq_msamples_per_s": n_in / (t1 - t0) / 1e6,
+            "decode_baseband_msamples_per_s": n_in / decim / (t2 - t1) / 1e6,
+            "realtime_channels_one_core": 1.0 / ((t2 - t0) / (n_in / decim / 48000.0))}
+
+
 def cpu_arm(steps: int, warmup: int, iq: np.ndarray | None = None, wl: "Workload | None" = None):
     """Oracle CPU implementation on the host cores (rank 0 only).  Returns (Msamples/s, ms/step, info).
     Each step is the full 1,024-stream batch of the GPU arm (about 8 core-seconds of work); for cfg5 a bounded
@@ -241,7 +258,8 @@ def cpu_arm(steps: int, warmup: int, iq: np.ndarray | None = None, wl: "Workload
     val = n_streams * N_PER_STEP / (ms * 1e-3) / 1e6
     info = {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port",
             "sample": f"all {n_streams} streams x {N_PER_STEP} samples per step ({steps} timed step(s)), {cores} threads, "
-                      f"oracle built {'-march=native' if native else '-march=x86-64-v3'}; the Rust reference cannot be built here"}
+                      f"oracle built {'-march=native' if native else '-march=x86-64-v3'}; the Rust reference cannot be built here",
+            "single_stream": single_stream_split(po, native, po.FMT_CF32, True, iq[0], DECIM)}
     return val, ms, info
 
 
@@ -268,7 +286,8 @@ def cpu_arm_cfg5(steps: int, warmup: int, wl: "Workload"):
     val = n_streams * wl.n / (ms * 1e-3) / 1e6
     return val, ms, {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port",
                      "sample": f"{n_streams} of the 65536 streams x {wl.n} u8 samples per step ({steps} timed step(s)), {cores} "
-                               f"threads, oracle built {'-march=native' if native else '-march=x86-64-v3'}; the Rust reference cannot be built here"}
+                               f"threads, oracle built {'-march=native' if native else '-march=x86-64-v3'}; the Rust reference cannot be built here",
+                     "single_stream": single_stream_split(po, native, po.FMT_U8, False, iq[0], wl.decim)}
 
 
 def config_dict(n_gpus: int):
