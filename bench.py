@@ -335,6 +335,7 @@ def run_b200(args):
     dev = tile_on_device(torch.from_numpy(wl.base()).cuda(), S, first=rank * S)
     host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
     host.copy_(dev)
+    torch.cuda.synchronize()          # the library runs on its own stream: inputs complete before they are handed over
     slots = 8 * (W + K) + 32
     ctx = p25.Context(S, fmt=p25.FMT_U8_IQ if wl.fmt == "u8" else p25.FMT_CF32_IQ, decimation=wl.decim, max_chunk_samples=n,
                       device=local, event_slots=slots)

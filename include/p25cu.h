@@ -113,7 +113,9 @@ const char* p25cu_last_error(const p25cu_ctx* ctx);
 
 /* ---- Surface 1: one DemodTask::run iteration for every stream (reference src/demod.rs:70-117).
  * iq: [n_streams][n_in_per_stream] samples of cfg.format, stream-major, contiguous.
- *     iq_on_device != 0: iq is a device pointer on cfg.device (no copy).
+ *     iq_on_device != 0: iq is a device pointer on cfg.device (no copy).  The library reads it on its own CUDA
+ *     stream: whatever produced the buffer must have completed (or the caller must have synchronised) before the
+ *     call, and the buffer must stay valid until the work is done (p25cu_sync / p25cu_poll).
  * baseband_out (nullable): host [n_streams][*n_out] float32; NULL keeps the result on the device
  *     for p25cu_decode(ctx, NULL, ...).
  * n_out: receives floor((n_in + phase) / decimation), the same for every stream.

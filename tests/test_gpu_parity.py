@@ -219,6 +219,7 @@ def test_demod_odd_chunks_and_device_input(p25, oracle):
     for m in (777, 12345, 20000, 6879):
         part = np.ascontiguousarray(np.stack([iq[pos:pos + m], iq[pos:pos + m][::-1]]))
         dev = torch.from_numpy(part.view(np.float32)).cuda()
+        torch.cuda.synchronize()      # the library reads the buffer on its own stream
         bb, n_out, _ = ctx.demod(dev, m)
         for s in range(2):
             ref = chains[s].feed(part[s])
@@ -542,9 +543,11 @@ def test_cfg5_full_size_properties(p25):
     total = dev.shape[1]
     cut = 22_016                                                             # multiple of 8: aligned fast path for chunk 2
     ctx = p25.Context(S_, fmt=p25.FMT_U8_IQ, decimation=5, max_chunk_samples=total, event_slots=64)
-    ctx.process(dev[:, :cut].contiguous(), cut)
+    part1, part2 = dev[:, :cut].contiguous(), dev[:, cut:].contiguous()
+    torch.cuda.synchronize()          # the library works on its own stream: the caller's producers must be done (C ABI contract)
+    ctx.process(part1, cut)
     ev1 = ctx.poll()
-    ctx.process(dev[:, cut:].contiguous(), total - cut)
+    ctx.process(part2, total - cut)
     ev = np.concatenate([ev1, ctx.poll()])
     ev = ev[np.lexsort((ev["sample"], ev["stream"]))]
     tsbk = ev[ev["kind"] == p25.EV_TSBK]
@@ -580,6 +583,7 @@ def test_cfg5_full_size_properties(p25):
     ctx.close()
     # (e) chunking invariance on a slice of the streams
     sub = dev[:4096].contiguous()
+    torch.cuda.synchronize()
     c1 = p25.Context(4096, fmt=p25.FMT_U8_IQ, decimation=5, max_chunk_samples=total, event_slots=64)
     c1.process(sub, total)
     one_shot = c1.poll()

@@ -76,6 +76,7 @@ def main():
         fmt, bps = p25.FMT_CF32_IQ, 8
     S, K, W = args.streams, args.steps, args.warmup
     dev = tile_on_device(base_dev, S)
+    torch.cuda.synchronize()          # the library runs on its own stream: the input must be complete before it is handed over
     ctx = p25.Context(S, fmt=fmt, decimation=args.decim, max_chunk_samples=n, device=0, event_slots=64 * (K + W + 6) // 2 + 64)
     stream = torch.cuda.ExternalStream(ctx.cuda_stream, device=0)
     for _ in range(W):

@@ -52,6 +52,7 @@ def main():
     chunk = np.tile(base.astype(np.complex64), args.chunk_ms // 150)
     caps = np.stack([np.roll(chunk, 400 * 77 * c) for c in range(args.captures)])
     dev = torch.from_numpy(caps.view(np.float32).reshape(args.captures, n, 2)).cuda()
+    torch.cuda.synchronize()
     S = 1536 * args.captures
     ctx = p25.Context(S, fmt=p25.FMT_CF32_IQ, decimation=400, max_chunk_samples=n, event_slots=64 * args.chunk_ms // 150 + 64)
     stream = torch.cuda.ExternalStream(ctx.cuda_stream, device=0)
