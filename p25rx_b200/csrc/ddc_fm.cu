@@ -690,6 +690,47 @@ __device__ __forceinline__ float disc_atan2(float y, float x) {
     return copysignf(r, y);
 }
 
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 fma2s(float2 a, float2 b, float c) {   // a * b + (c, c)
+    unsigned long long r;
+    const float2 cc = make_float2(c, c);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<const unsigned long long*>(&cc)));
+    return *reinterpret_cast<float2*>(&r);
+}
+// disc_atan2 for two outputs at once: the polynomial and the three multiplies run packed (same arithmetic per half)
+__device__ __forceinline__ float2 disc_atan2_pair(float2 y, float2 x) {
+    const float ax0 = fabsf(x.x), ay0 = fabsf(y.x), ax1 = fabsf(x.y), ay1 = fabsf(y.y);
+    const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0), mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
+    float rc0, rc1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc0) : "f"(fmaxf(mx0, 1e-30f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc1) : "f"(fmaxf(mx1, 1e-30f)));
+    const float2 t = mul2(make_float2(mn0, mn1), make_float2(rc0, rc1)), u = mul2(t, t);
+    float2 q = make_float2(-0.004295386839658022f, -0.004295386839658022f);
+    q = fma2s(q, u, 0.022737378254532814f);
+    q = fma2s(q, u, -0.057179518043994904f);
+    q = fma2s(q, u, 0.09735459089279175f);
+    q = fma2s(q, u, -0.13945257663726807f);
+    q = fma2s(q, u, 0.1995391547679901f);
+    q = fma2s(q, u, -0.3333050608634949f);
+    q = fma2s(q, u, 0.9999995231628418f);
+    const float2 r = mul2(q, t);
+    float r0 = r.x, r1 = r.y;
+    r0 = ay0 > ax0 ? 1.57079632679489662f - r0 : r0;
+    r1 = ay1 > ax1 ? 1.57079632679489662f - r1 : r1;
+    r0 = x.x < 0.f ? 3.14159265358979324f - r0 : r0;
+    r1 = x.y < 0.f ? 3.14159265358979324f - r1 : r1;
+    return make_float2(copysignf(r0, y.x), copysignf(r1, y.y));
+}
+
 // 5R u8 samples starting at half-word ODD of wp[0] -> floats in byte units centred on 128
 template <int R, bool ODD>
 __device__ __forceinline__ void load_u8(const unsigned* __restrict__ wp, float2 (&x)[5 * R]) {
@@ -920,7 +961,7 @@ using fast::mbar_expect_tx;
 using fast::mbar_wait;
 using fast::tma_load_1d;
 using fast5::add2;
-using fast5::disc_atan2;
+using fast5::disc_atan2_pair;
 using fast5::load_u8;
 
 constexpr int R = 4;                        // outputs per lane
@@ -1102,14 +1143,18 @@ __global__ void __launch_bounds__(32 * WARPS, Fmt<FMT>::MINB) p25_ddc5_warp_kern
         c_carry.x = __shfl_sync(0xFFFFFFFFu, acc[R - 1].x, 30);
         c_carry.y = __shfl_sync(0xFFFFFFFFu, acc[R - 1].y, 30);
         float dd[R];
+        static_assert(R % 2 == 0, "the discriminator runs on output pairs");
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const float2 cu = acc[r];
-            const float re = cu.x * prev.x + cu.y * prev.y;
-            const float im = cu.y * prev.x - cu.x * prev.y;
-            dd[r] = disc_atan2(im, re) * P25_FM_GAIN;
-            if (want_pw && R * lane + r < nv) pw += cu.x * cu.x + cu.y * cu.y;
-            prev = cu;
+        for (int r = 0; r < R; r += 2) {
+            const float2 c0 = acc[r], c1 = acc[r + 1];
+            const float2 re = make_float2(c0.x * prev.x + c0.y * prev.y, c1.x * c0.x + c1.y * c0.y);
+            const float2 im = make_float2(c0.y * prev.x - c0.x * prev.y, c1.y * c0.x - c1.x * c0.y);
+            const float2 th = disc_atan2_pair(im, re);
+            dd[r] = th.x * P25_FM_GAIN;
+            dd[r + 1] = th.y * P25_FM_GAIN;
+            if (want_pw && R * lane + r < nv) pw += c0.x * c0.x + c0.y * c0.y;
+            if (want_pw && R * lane + r + 1 < nv) pw += c1.x * c1.x + c1.y * c1.y;
+            prev = c1;
         }
         sm.d4[DROWS + lane] = make_float4(dd[0], dd[1], dd[2], dd[3]);
         __syncwarp();                                                                 // S2
