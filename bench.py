@@ -173,8 +173,14 @@ class StreamGate:
     steady-state producer sees -- instead of inheriting the scheduling jitter of eight Python ranks sharing one host.
     Falls back to no gate if the driver API is unavailable."""
 
-    def __init__(self, stream_handle: int):
+    def __init__(self, stream_handle: int, enabled: bool = True):
         self.ok = False
+        # A closed gate deadlocks anything that makes launches synchronous (a profiler replaying kernels one by one,
+        # CUDA_LAUNCH_BLOCKING): never gate then, and a watchdog opens the gate after 250 ms whatever happens.
+        blocking = os.environ.get("CUDA_LAUNCH_BLOCKING", "0") not in ("", "0")
+        injected = any(k.startswith(("CUDA_INJECTION", "NV_COMPUTE_PROFILER", "NSIGHT", "NV_NSIGHT", "NVTX_INJECTION")) for k in os.environ)
+        if not enabled or blocking or injected:
+            return
         try:
             import torch
             import warnings
@@ -185,6 +191,10 @@ class StreamGate:
             err, = drv.cuStreamWaitValue32(drv.CUstream(stream_handle), drv.CUdeviceptr(self.flag.data_ptr()), 1,
                                            drv.CUstreamWaitValue_flags.CU_STREAM_WAIT_VALUE_GEQ)
             self.ok = int(err) == 0
+            if self.ok:
+                self.watchdog = threading.Timer(0.25, self.open)
+                self.watchdog.daemon = True
+                self.watchdog.start()
         except Exception:
             self.ok = False
 
@@ -359,7 +369,7 @@ def run_b200(args):
     sampler.start()
     t_host0 = time.perf_counter()
     with torch.cuda.stream(stream):
-        gate = StreamGate(ctx.cuda_stream)               # the device starts when the launch queue holds the first steps
+        gate = StreamGate(ctx.cuda_stream, enabled=not args.no_gate)   # the device starts when the launch queue holds the first steps
         t_begin.record(stream)
         for k in range(K):
             if k == 48:
@@ -470,6 +480,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-gate", action="store_true", help="do not hold the stream back while the timed steps are enqueued")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
                     help="cfg2 (default): 1,024 cf32 2.4 MS/s streams per GPU; cfg5: 65,536 u8 240 kS/s streams over all GPUs")
     args = ap.parse_args()
