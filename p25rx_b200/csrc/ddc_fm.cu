@@ -9,18 +9,23 @@
 //   10-tap moving average           src/demod.rs:114     (moving_avg::MovingAverage::new(10))
 // plus a /10 front stage for 2.4 MS/s input (BASELINE.json configs[0]; declared extension).
 //
-// Design.  The whole chain is non-recursive, so every output is a pure function of a window of
-// the logical input (tail of the previous chunk ++ this chunk).  A CTA owns one (stream, segment)
-// and streams through it in blocks: the block is staged in shared memory with coalesced 16-byte
-// loads, then each decimating stage runs *input-stationary*: a thread reads its own D consecutive
-// inputs once (conflict-free LDS.128 / LDS.64), forms the Q partial sums that those inputs
-// contribute to the next Q outputs with the taps as constant-bank operands, and neighbouring
-// partials are combined through shared memory.  Every staged input is therefore read from shared
-// memory exactly once.  The 48 kHz stages (channel FIR, discriminator, boxcar) use power-of-two
-// rings.  A segment starts one block early to warm the rings up, so segments are independent and
-// the only carried state is the raw input tail.
+// The whole chain is non-recursive, so every output is a pure function of a window of the logical
+// input (tail of the previous chunk ++ this chunk); the only carried state is that raw input tail,
+// kept in the stream's own sample format.  Four kernels share the arithmetic:
 //
-// HBM-bound by design: algorithmic traffic 8 + 4/D bytes per cf32 input sample.
+//   p25_ddc_fm_kernel<FRONT,FMT>      generic: any length and alignment, the first chunk of a stream
+//                                     (implicit zeros in front of it), odd chunks.  A CTA owns one
+//                                     (stream, segment), stages blocks with coalesced loads (u8 through
+//                                     a shared-memory copy of the table), runs the decimating stages
+//                                     input-stationary and the 48 kHz stages on power-of-two rings.
+//   fast::p25_ddc_fm_stream_kernel    cf32, /50 (the bench kernel): TMA bulk copies into a two-stage
+//                                     ring, FFMA2 FIRs, persistent grid with a static + ticket work split.
+//   fast5::p25_ddc5_fm_kernel<FMT>    /5 tile kernel: independent tiles with their own warm-up.
+//   w5::p25_ddc5_warp_kernel<FMT>     /5 warp-autonomous kernel (default for u8 and cf32): every warp is
+//                                     its own pipeline, no CTA barriers.
+//
+// Algorithmic traffic: 8 + 4/D bytes per cf32 input sample, 2 + 4/D per u8 sample; the /50
+// kernel is HBM-bound, the /5 kernels are bound by the FP32 pipe (66 complex-by-real taps per output).
 #include <stdlib.h>
 
 #include "p25cu_internal.cuh"

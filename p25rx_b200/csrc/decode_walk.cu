@@ -5,15 +5,21 @@
 // (crate p25 @a96c564, not vendored).  One warp owns one stream.  Instead of stepping one
 // sample at a time the warp advances in bulk between "decision points":
 //
-//   SYNC    32 candidate positions per step; every lane evaluates the 231-tap frame-sync
-//           correlation and window energy of one position, neighbouring results travel by
-//           warp shuffle and the first lane whose predicate fires is found with a ballot.
-//   symbols 32 symbol instants per step (stride 10 samples); lanes slice their sample
-//           against the three thresholds, a ballot removes status symbols (every 36th
-//           dibit) and gives each data dibit its index in the unit buffer.
-//   unit    when the dibit that completes a NID / TSBK block / voice frame / ... has been
-//           stored, lane 0 runs the FEC decoder and writes the event; state is shared
-//           through the warp's shared-memory record.
+//   SYNC    128 candidate positions per step, four consecutive ones per lane: the 231-tap frame-sync
+//           correlation and the window energy of every position run on packed FFMA2 from a register
+//           window fed by 16-byte shared-memory loads; the first position whose predicate fires is
+//           found with a warp-wide minimum, the predecessor of a lane's first position by shuffle.
+//   symbols 64 symbol instants per step (stride 10 samples); lanes slice their samples against the
+//           three thresholds, a ballot removes status symbols (every 36th dibit) and gives each
+//           data dibit its index in the unit buffer.
+//   unit    when the dibit that completes a NID / TSBK block / voice frame / ... has been stored the
+//           warp decodes it cooperatively (BCH syndromes and Chien search per lane, Viterbi on 16
+//           lanes, IMBE / Golay / Hamming / cyclic words one per lane, Reed-Solomon with per-lane
+//           syndromes and Chien/Forney); lane 0 alone touches the receiver state, the stats and
+//           queues the event, which the warp writes out 20 lanes wide.
+//
+// The grid covers the streams in one pass, or -- beside the next chunk's demod kernel -- is a
+// persistent grid of two CTAs per SM that walks them in several passes (p25cu_launch_walk).
 //
 // Every step is an exact restatement of the sample-at-a-time rule (oracle/p25_oracle.cpp),
 // so events and their sample indices are bit-identical for any chunking.  This file is
