@@ -57,7 +57,7 @@ typedef struct {
     uint32_t n_streams;         /* independent streams held by this context */
     int32_t format;             /* p25cu_format */
     int32_t decimation;         /* 5 or 50 */
-    uint64_t max_chunk_samples; /* largest n_in_per_stream (demod) this context will be given */
+    uint64_t max_chunk_samples; /* largest n_in_per_stream (demod) this context will be given (at most 2^30) */
     uint64_t max_baseband;      /* largest n_per_stream for p25cu_decode of caller-provided baseband;
                                    0 = derive from max_chunk_samples / decimation */
     uint32_t abi_version;       /* P25CU_ABI_VERSION */

@@ -227,6 +227,7 @@ extern "C" int p25cu_create(const p25cu_config* cfg, p25cu_ctx** out) {
     }
     *out = nullptr;
     if (cfg->abi_version != P25CU_ABI_VERSION || cfg->n_streams == 0 || cfg->max_chunk_samples == 0 ||
+        cfg->max_chunk_samples > (1ull << 30) || cfg->max_baseband > (1ull << 30) ||   /* kernels index a chunk with 32-bit ints */
         (cfg->decimation != 5 && cfg->decimation != 50 && cfg->decimation != (int)p25cu_pfb_decimation()) ||
         (cfg->format != P25CU_FMT_U8_IQ && cfg->format != P25CU_FMT_CF32_IQ) ||
         (cfg->decimation == (int)p25cu_pfb_decimation() &&
