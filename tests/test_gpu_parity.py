@@ -591,3 +591,31 @@ def test_cfg5_full_size_properties(p25):
     two = ev[ev["stream"] < 4096]
     assert events_key(one_shot) == events_key(two)
     assert co.TsbkFields(bytes(tsbk[good]["payload"][0][:12])).crc_valid()
+
+
+def test_demod_weak_and_strong_u8_signals(p25, oracle):
+    """The /5 u8 kernel works in byte units centred on 128 and restores the 0.5-LSB offset as a constant after the
+    filters: check the tolerance where that matters most -- a carrier of only +-4 LSB -- and near full scale."""
+    st = tx.control_channel(321, 3)
+    S_ = 4
+    amps = [0.03, 0.06, 0.5, 0.95]
+    rows = [tx.iq_to_u8(tx.modulate_iq(st.dibits, 240_000, snr_db=25, cfo_hz=200.0 * (s - 1.5), seed=s, amplitude=a))
+            for s, a in enumerate(amps)]
+    n = min(len(r) for r in rows) // 2 // 8 * 8
+    data = np.stack([r[: 2 * n] for r in rows])
+    ctx = p25.Context(S_, fmt=p25.FMT_U8_IQ, decimation=5, max_chunk_samples=n)
+    cut = 16384
+    got, pws = [], []
+    for a, b in ((0, cut), (cut, n)):                              # generic kernel, then the warp kernel
+        bb, _, pw = ctx.demod(np.ascontiguousarray(data[:, 2 * a: 2 * b]), b - a, want_power=True)
+        got.append(bb)
+        pws.append(pw)
+    got = np.concatenate(got, axis=1)
+    for s in range(S_):
+        chain = oracle.DemodChain(oracle.FMT_U8, False)
+        r1, p1 = chain.feed(data[s, : 2 * cut], want_power=True)
+        r2, p2 = chain.feed(data[s, 2 * cut:], want_power=True)
+        ref = np.concatenate([r1, r2])
+        assert np.max(np.abs(got[s] - ref)) < BB_TOL, (amps[s], float(np.max(np.abs(got[s] - ref))))
+        assert abs(pws[0][s] - p1) < 1e-2 and abs(pws[1][s] - p2) < 1e-2
+    ctx.close()
