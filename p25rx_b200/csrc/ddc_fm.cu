@@ -417,7 +417,14 @@ __device__ __forceinline__ void issue_block(Smem& sm, int stage, const DdcParams
 // CTA, no extra warm-ups) and a dynamic remainder handed out in DYN_CH-block tickets.  A CTA that becomes resident
 // late -- the previous chunk's walker CTAs still hold registers and shared memory on its SM -- simply draws fewer
 // tickets instead of stretching the whole launch (with a purely static split that tail cost ~9 % beside the walker).
-constexpr unsigned DYN_CH = 16;
+#ifndef DDC50_DYN_CH
+#define DDC50_DYN_CH 16
+#endif
+#ifndef DDC50_STATIC_NUM
+#define DDC50_STATIC_NUM 7
+#define DDC50_STATIC_DEN 8
+#endif
+constexpr unsigned DYN_CH = DDC50_DYN_CH;
 
 #ifndef DDC50_MAXREG
 #define DDC50_MAXREG 56
@@ -1260,7 +1267,7 @@ static cudaError_t launch_fast(const DdcParams& p, cudaStream_t st) {
     const unsigned grid = total < (unsigned long long)grid_cache ? (unsigned)total : (unsigned)grid_cache;
     // 7/8 of the blocks are split statically, the rest goes out in tickets; the ticket counter only ever grows, every
     // launch consumes n_tickets + grid draws (each CTA stops at its first out-of-range ticket)
-    const unsigned n_static = (unsigned)(total / grid * 7 / 8);
+    const unsigned n_static = (unsigned)(total / grid * DDC50_STATIC_NUM / DDC50_STATIC_DEN);
     const unsigned long long dyn = total - (unsigned long long)n_static * grid;
     const unsigned n_tickets = (unsigned)((dyn + fast::DYN_CH - 1) / fast::DYN_CH);
     fast::p25_ddc_fm_stream_kernel<<<grid, fast::NT, smem, st>>>(p, bps, n_static, n_tickets, *p.ticket_base);
