@@ -58,6 +58,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--snr", type=float, default=20.0)
     ap.add_argument("--n-base", type=int, default=16)
+    ap.add_argument("--periods", type=int, default=1, help="periods of the transmission per step (longer chunks per call)")
     args = ap.parse_args()
 
     import torch
@@ -66,6 +67,8 @@ def main():
 
     fs = 48000 * args.decim
     base = base_streams(args.kind, fs, args.n_base, args.snr)
+    if args.periods > 1:
+        base = np.tile(base, (1, args.periods))
     n = base.shape[1]
     if args.fmt == "u8":
         b8 = np.stack([tx.iq_to_u8(b).reshape(n, 2) for b in base])
@@ -77,7 +80,8 @@ def main():
     S, K, W = args.streams, args.steps, args.warmup
     dev = tile_on_device(base_dev, S)
     torch.cuda.synchronize()          # the library runs on its own stream: the input must be complete before it is handed over
-    ctx = p25.Context(S, fmt=fmt, decimation=args.decim, max_chunk_samples=n, device=0, event_slots=64 * (K + W + 6) // 2 + 64)
+    ctx = p25.Context(S, fmt=fmt, decimation=args.decim, max_chunk_samples=n, device=0,
+                      event_slots=(32 * (K + W + 6) + 64) * args.periods)
     stream = torch.cuda.ExternalStream(ctx.cuda_stream, device=0)
     for _ in range(W):
         ctx.process(dev, n)
