@@ -619,3 +619,32 @@ def test_demod_weak_and_strong_u8_signals(p25, oracle):
         assert np.max(np.abs(got[s] - ref)) < BB_TOL, (amps[s], float(np.max(np.abs(got[s] - ref))))
         assert abs(pws[0][s] - p1) < 1e-2 and abs(pws[1][s] - p2) < 1e-2
     ctx.close()
+
+
+def test_replay_tool_prints_consumer_view(p25, tmp_path):
+    """tools/p25replay.py: the `p25rx -r FILE` shape as a command, JSON lines with the fields the consumers read."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from p25rx_b200 import consumers as co
+    st = tx.control_channel(55, 3)
+    bb, _ = tx.baseband_48k(st.dibits, snr_db=22, seed=3)
+    f32 = tmp_path / "cc.f32"
+    with open(f32, "wb") as f:
+        co.write_baseband(f, bb)
+    raw = tx.iq_to_u8(tx.modulate_iq(st.dibits, 240_000, snr_db=25, seed=4, amplitude=0.4))
+    u8 = tmp_path / "cc.u8"
+    raw[: 32768 * (len(raw) // 32768)].tofile(u8)
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "p25replay.py")
+    for argv, n_tsbk in (([str(f32)], 9), (["--iq", str(u8)], 6)):
+        r = subprocess.run([sys.executable, tool] + argv, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1500:]
+        lines = [json.loads(x) for x in r.stdout.splitlines()]
+        tsbk = [x for x in lines if x["event"] == "TrunkingControl"]
+        assert len(tsbk) >= n_tsbk and all(x["crc_valid"] and x["mfg"] == 0 for x in tsbk)
+        assert [x for x in lines if x["event"] == "PacketNID"][0]["nac"] == 0x293
+        stats = [x for x in lines if x["event"] == "stats"][0]["stats"]
+        assert stats["viterbiDibit"]["totalWords"] == len(tsbk) and stats["bch"]["totalWords"] >= 2
+        if "--iq" in argv:
+            assert any(x["event"] == "sigPower" for x in lines)
