@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define P25CU_ABI_VERSION 1
+#define P25CU_ABI_VERSION 1   /* additions since round 1 are new entry points only; existing signatures are unchanged */
 
 typedef enum {
     P25CU_OK = 0,
@@ -45,7 +45,7 @@ typedef enum { P25CU_FMT_U8_IQ = 0, P25CU_FMT_CF32_IQ = 1 } p25cu_format;
 
 /* Decimation from the input rate to the 48 kHz baseband rate (reference src/consts.rs:11-13).
  * 5   : 240 kS/s input, the reference's own chain               (reference src/demod.rs:50)
- * 50  : 2.4 MS/s input, a /10 front stage ahead of the same chain (BASELINE.json configs[0])
+ * 50  : 2.4 MS/s input, a /10 front stage ahead of the same chain (BASELINE.json configs[0]); cf32 or u8
  * 400 : wideband channelizer (BASELINE.json configs[2]; declared extension, the reference has one tuner and one
  *       channel, src/sdr.rs:61-68): every input row is a 19.2 MS/s cf32 capture that a polyphase filter bank splits
  *       into 1,536 channels 12.5 kHz apart, each delivered at 48 kS/s and run through the reference's 48 kHz stages
@@ -82,6 +82,9 @@ typedef enum {
     P25CU_E_BCH = 1, P25CU_E_RS = 2, P25CU_E_VITERBI_DIBIT = 3, P25CU_E_VITERBI_TRIBIT = 4, P25CU_E_UNKNOWN_NID = 5
 } p25cu_error_code;
 
+/* Packet data units (DUID 0xC) are received -- header block, then the data blocks it announces, 3/4-rate trellis for
+ * confirmed data, 1/2-rate otherwise -- but no MessageEvent variant carries packet data (src/recv.rs:214-233): they
+ * only show up in the viterbiDibit / viterbiTribit stats (src/hub.rs:569-570) and as P25CU_E_VITERBI_* errors. */
 typedef struct {
     uint32_t stream;     /* stream index within the context */
     uint32_t kind;       /* p25cu_event_kind */
@@ -113,9 +116,14 @@ const char* p25cu_last_error(const p25cu_ctx* ctx);
 
 /* ---- Surface 1: one DemodTask::run iteration for every stream (reference src/demod.rs:70-117).
  * iq: [n_streams][n_in_per_stream] samples of cfg.format, stream-major, contiguous.
+ *     iq_on_device == 0: host memory.  The chunk is copied to one of two device staging buffers on a copy stream, so
+ *     the copy of chunk k+1 runs beside the kernels of chunk k; the call returns when ITS copy has completed: the
+ *     caller may refill the buffer immediately (like a Checkout going back to the reference's pool, src/demod.rs:70).
+ *     Pinned memory (p25cu_host_alloc / p25cu_host_register) is copied by DMA at full PCIe rate; pageable memory is
+ *     staged by the driver.
  *     iq_on_device != 0: iq is a device pointer on cfg.device (no copy).  The library reads it on its own CUDA
  *     stream: whatever produced the buffer must have completed (or the caller must have synchronised) before the
- *     call, and the buffer must stay valid until the work is done (p25cu_sync / p25cu_poll).
+ *     call, and the buffer must stay valid and unmodified until the work is done (p25cu_sync / p25cu_poll).
  * baseband_out (nullable): host [n_streams][*n_out] float32; NULL keeps the result on the device
  *     for p25cu_decode(ctx, NULL, ...).
  * n_out: receives floor((n_in + phase) / decimation), the same for every stream.
@@ -126,9 +134,12 @@ int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n_in_per_stream, int iq_o
 
 /* ---- Surface 2: MessageReceiver::feed over a chunk of every stream (reference src/recv.rs:204-234,
  * src/replay.rs:40-57).
- * baseband: host [n_streams][n_per_stream] float32 at 48 kHz, or NULL to consume the device-resident
- *     output of the preceding p25cu_demod (n_per_stream is then ignored).
- * Events are queued inside ctx until p25cu_poll. */
+ * baseband: host [n_streams][n_per_stream] float32 at 48 kHz (copied before the call returns), or NULL to consume the
+ *     device-resident output of the preceding p25cu_demod (n_per_stream is then ignored).  Only the newest demodulated
+ *     chunk stays on the device: once decoding has begun, a p25cu_decode(NULL) that finds more than one undecoded
+ *     chunk returns P25CU_ERR_STATE (event sample indices and the sync history assume a gap-free stream).  A context
+ *     used for demodulation only (p25cu_demod with baseband_out, never decoded) is fine.
+ * Events are queued inside ctx until a poll. */
 int p25cu_decode(p25cu_ctx* ctx, const float* baseband, size_t n_per_stream);
 
 /* p25cu_demod followed by p25cu_decode of its device-resident output, one call (the hot path). */
@@ -143,6 +154,33 @@ int p25cu_poll(p25cu_ctx* ctx, p25cu_event* out, size_t cap, size_t* n);
 int p25cu_poll_view(p25cu_ctx* ctx, const p25cu_event** events, size_t* n);
 /* Number of events p25cu_poll would return now (waits for queued GPU work). */
 int p25cu_pending(p25cu_ctx* ctx, size_t* n);
+
+/* ---- Packed, asynchronous event drain (the production path for many thousands of channels).
+ * Records are variable-length, 32-bit aligned, ordered by (stream, sample):
+ *     word 0            stream
+ *     word 1            sample, bits 0..31
+ *     word 2            sample bits 32..47 | kind << 16 | len << 24
+ *     ceil(len / 4) payload words (bytes beyond len are zero)
+ * i.e. a PacketNID takes 16 bytes and a TSBK 24 instead of 80.
+ * p25cu_poll_start queues the compaction of everything decoded so far behind the work already submitted and returns at
+ * once; the compaction kernel writes the records straight into pinned host memory, so no separate copy follows and
+ * the next chunk's kernels run beside it.  At most two started polls may be outstanding.
+ * p25cu_poll_packed collects the oldest started poll (starting one first if none is outstanding) and waits for it only.
+ * *words points at ctx-owned pinned memory, valid until two further polls have been started.  *more (nullable) is set
+ * when the host buffer (256 MiB) could not hold every queued event: the remaining streams' events come with the next poll.
+ * Do not interleave with p25cu_poll / p25cu_poll_view while a started poll is outstanding (P25CU_ERR_STATE). */
+int p25cu_poll_start(p25cu_ctx* ctx);
+int p25cu_poll_packed(p25cu_ctx* ctx, const uint32_t** words, size_t* n_words, size_t* n_events, int* more);
+/* Expand packed records into p25cu_event records on the host (no GPU work).  *n receives the number written. */
+int p25cu_unpack_events(const uint32_t* words, size_t n_words, p25cu_event* out, size_t cap, size_t* n);
+
+/* ---- Pinned host buffers for sample chunks: the counterpart of the reference's buffer pools (src/demod.rs:63, :103;
+ * src/sdr.rs:25-33).  p25cu_host_alloc returns page-locked memory; p25cu_host_register page-locks memory the caller
+ * already owns (e.g. a Rust Vec<u8>), p25cu_host_unregister releases it. */
+int p25cu_host_alloc(p25cu_ctx* ctx, size_t bytes, void** out);
+int p25cu_host_free(p25cu_ctx* ctx, void* p);
+int p25cu_host_register(p25cu_ctx* ctx, void* p, size_t bytes);
+int p25cu_host_unregister(p25cu_ctx* ctx, void* p);
 
 /* MessageReceiver::resync (reference src/recv.rs:136, :179): takes effect at the next chunk. */
 int p25cu_resync(p25cu_ctx* ctx, uint32_t stream);
@@ -167,6 +205,10 @@ int p25cu_demod_timing(p25cu_ctx* ctx, int enable, double* avg_ms, unsigned* cou
 /* Device pointer/row stride (in floats) of the baseband produced by the last p25cu_demod. */
 int p25cu_device_baseband(p25cu_ctx* ctx, const float** ptr, size_t* row_stride, size_t* n_out);
 
+/* Copy the first n baseband samples of one stream of the last p25cu_demod / p25cu_process to the host (parity tests
+ * sample a few streams of a large batch this way). */
+int p25cu_read_baseband(p25cu_ctx* ctx, uint32_t stream, float* out, size_t n);
+
 /* Channelizer mode only: copy the channel spectra of the last p25cu_demod, [captures][*n_rows][1536] complex float32
  * (48 kS/s per channel, before the channel-select filter), to `out` (nullable: only report *n_rows). */
 int p25cu_channelizer_output(p25cu_ctx* ctx, float* out, size_t* n_rows);
@@ -178,7 +220,8 @@ int p25cu_channelizer_output(p25cu_ctx* ctx, float* out, size_t* n_rows);
  *       7 rs (n,k) on `count` blocks of n bytes, corrected in place in `words`
  *       8 half-rate trellis: `count` blocks of 98 dibit bytes -> 12 bytes each in out_data
  *       9 imbe: `count` blocks of 72 dibit bytes -> 15 uint32 each in out_data
- *       10..13: the warp-cooperative forms the decode walker uses (one warp per word) of kinds 7, 9, 0, 8 */
+ *       10..13: the warp-cooperative forms the decode walker uses (one warp per word) of kinds 7, 9, 0, 8
+ *       14 3/4-rate trellis: `count` blocks of 98 dibit bytes -> 18 bytes each in out_data; 15 its warp-cooperative form */
 int p25cu_fec_selftest(p25cu_ctx* ctx, int kind, void* words, size_t count, int n, int k,
                        void* out_data, int32_t* out_nerr);
 

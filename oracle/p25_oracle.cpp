@@ -235,7 +235,7 @@ int rs_decode(uint8_t* sym, int n, int k) {
 // ===========================================================================
 // Half-rate trellis (TSBK)  [STD]; surfaces as TrunkingControl, src/recv.rs:231
 // ===========================================================================
-#define P25_VITERBI_MAX_FIX 18  /* random blocks never get below ~22 (tests/test_oracle_fec.py) */
+
 int trellis_half_decode(const uint8_t* dibits98, uint8_t* out12) {
     uint8_t sym[49];
     for (int i = 0; i < 49; i++) {
@@ -272,6 +272,53 @@ int trellis_half_decode(const uint8_t* dibits98, uint8_t* out12) {
     }
     std::memset(out12, 0, 12);
     for (int i = 0; i < 48; i++) out12[i / 4] |= (uint8_t)(in[i] << (6 - 2 * (i % 4)));
+    return m[0];
+}
+
+// ===========================================================================
+// 3/4-rate trellis (confirmed packet data blocks)  [STD]; surfaces only as the viterbiTribit stats family
+// (src/hub.rs:570) and P25Error -- no MessageEvent variant carries packet data (src/recv.rs:214-233).
+// 8 states (the previous tribit), 49 steps (48 tribits + the flush tribit), same interleaver as the 1/2-rate code.
+// ===========================================================================
+int trellis_34_decode(const uint8_t* dibits98, uint8_t* out18) {
+    uint8_t sym[49];
+    for (int i = 0; i < 49; i++) {
+        const int slot = P25_INTERLEAVE[i];
+        sym[i] = (uint8_t)((dibits98[2 * slot] << 2) | dibits98[2 * slot + 1]);
+    }
+    const int INF = 1 << 20;
+    int m[8] = {0, INF, INF, INF, INF, INF, INF, INF};
+    uint8_t from[49][8];
+    for (int i = 0; i < 49; i++) {
+        int nm[8];
+        for (int ns = 0; ns < 8; ns++) {
+            int best = 2 * INF, arg = 0;
+            for (int ps = 0; ps < 8; ps++) {
+                const int expect = P25_CONSTELLATION[P25_TRELLIS_3_4[ps * 8 + ns]];
+                const int cost = m[ps] + __builtin_popcount(expect ^ sym[i]);
+                if (cost < best) {  // ties keep the lowest predecessor state
+                    best = cost;
+                    arg = ps;
+                }
+            }
+            nm[ns] = best;
+            from[i][ns] = (uint8_t)arg;
+        }
+        std::memcpy(m, nm, sizeof m);
+    }
+    if (m[0] > P25_VITERBI34_MAX_FIX) return -1;  // the flush tribit forces state 0
+    uint8_t in[49];
+    int st = 0;
+    for (int i = 48; i >= 0; i--) {
+        in[i] = (uint8_t)st;
+        st = from[i][st];
+    }
+    std::memset(out18, 0, 18);
+    for (int i = 0; i < 48; i++)
+        for (int b = 0; b < 3; b++) {
+            const int bit = 3 * i + b;
+            out18[bit >> 3] |= (uint8_t)(((in[i] >> (2 - b)) & 1) << (7 - (bit & 7)));
+        }
     return m[0];
 }
 
@@ -480,8 +527,8 @@ bool MessageReceiver::on_nid(uint64_t idx, Event* ev) {
         case 0x3:
             state_ = ST_FLUSH;
             break;
-        case 0xC:  // packet data carries no MessageEvent (src/recv.rs:214-233): drop lock
-            enter_sync();
+        case 0xC:  // packet data: header block, then the data blocks it announces; none of them yields a
+            state_ = ST_PAYLOAD;  // MessageEvent (src/recv.rs:214-233), only stats and errors
             break;
         default:
             return fail(ERR_UNKNOWN_NID, idx, ev);
@@ -526,6 +573,47 @@ bool MessageReceiver::on_payload(uint64_t idx, Event* ev) {
             if ((out[0] & 0x80) || blocks_ == 3) state_ = ST_FLUSH;
             fill(ev, EV_TSBK, idx, out, 12);  // emitted before any CRC check (src/recv.rs:242)
             return true;
+        }
+        case 0xC: {  // PDU: 98-dibit blocks.  blocks_ = blocks decoded, part_ = data blocks announced, chunks_ = confirmed
+            if (cnt_ < P25_TSBK_DIBITS) return false;
+            cnt_ = 0;
+            if (blocks_ == 0) {  // header block, always 1/2-rate [STD]
+                uint8_t h[12];
+                const int fixed = trellis_half_decode(buf_, h);
+                if (fixed < 0) {
+                    stats.bad(ST_VITERBI_DIBIT);
+                    return fail(ERR_VITERBI_DIBIT, idx, ev);
+                }
+                stats.ok(ST_VITERBI_DIBIT, (unsigned)fixed);
+                if (crc_ccitt_p25(h, 10) != (uint16_t)((h[10] << 8) | h[11])) {
+                    enter_sync();  // the length field cannot be trusted: drop lock (no P25Error names a CRC)
+                    return false;
+                }
+                blocks_ = 1;
+                part_ = h[6] & 0x7F;
+                chunks_ = (h[0] & 0x1F) == P25_PDU_FORMAT_CONFIRMED;
+                if (part_ == 0) state_ = ST_FLUSH;
+                return false;
+            }
+            if (chunks_) {  // confirmed data: 3/4-rate blocks
+                uint8_t d[18];
+                const int fixed = trellis_34_decode(buf_, d);
+                if (fixed < 0) {
+                    stats.bad(ST_VITERBI_TRIBIT);
+                    return fail(ERR_VITERBI_TRIBIT, idx, ev);
+                }
+                stats.ok(ST_VITERBI_TRIBIT, (unsigned)fixed);
+            } else {
+                uint8_t d[12];
+                const int fixed = trellis_half_decode(buf_, d);
+                if (fixed < 0) {
+                    stats.bad(ST_VITERBI_DIBIT);
+                    return fail(ERR_VITERBI_DIBIT, idx, ev);
+                }
+                stats.ok(ST_VITERBI_DIBIT, (unsigned)fixed);
+            }
+            if (++blocks_ == 1 + part_) state_ = ST_FLUSH;
+            return false;
         }
         case 0x0: {  // HDU
             if (cnt_ < P25_HDU_DIBITS) return false;
@@ -681,6 +769,7 @@ int p25o_hamming10_decode(uint32_t w, uint32_t* d) { return hamming10_decode(w, 
 int p25o_cyclic16_decode(uint32_t w, uint32_t* d) { return cyclic16_decode(w, d); }
 int p25o_rs_decode(uint8_t* sym, int n, int k) { return rs_decode(sym, n, k); }
 int p25o_trellis_half_decode(const uint8_t* d98, uint8_t* out12) { return trellis_half_decode(d98, out12); }
+int p25o_trellis_34_decode(const uint8_t* d98, uint8_t* out18) { return trellis_34_decode(d98, out18); }
 void p25o_imbe_decode(const uint8_t* d72, uint32_t* chunks8, uint32_t* errors7) { imbe_decode(d72, chunks8, errors7); }
 uint32_t p25o_crc_ccitt(const uint8_t* d, int n) { return crc_ccitt_p25(d, n); }
 

@@ -100,6 +100,8 @@ int cyclic16_decode(uint32_t word, uint32_t* data8);
 int rs_decode(uint8_t* sym, int n, int k);
 // half-rate trellis: 98 received dibits -> 12 bytes.  returns corrected bit count or -1.
 int trellis_half_decode(const uint8_t* dibits98, uint8_t* out12);
+// 3/4-rate trellis: 98 received dibits -> 18 bytes.  returns corrected bit count or -1.
+int trellis_34_decode(const uint8_t* dibits98, uint8_t* out18);
 // IMBE frame: 72 received dibits -> u0..u7 and 7 error counts.
 void imbe_decode(const uint8_t* dibits72, uint32_t chunks[8], uint32_t errors[7]);
 uint16_t crc_ccitt_p25(const uint8_t* data, int n);

@@ -57,6 +57,7 @@ def lib(native: bool = False) -> C.CDLL:
         getattr(L, f"p25o_{n}_decode").argtypes = [C.c_uint32, u32p]
     L.p25o_rs_decode.argtypes = [vp, C.c_int, C.c_int]
     L.p25o_trellis_half_decode.argtypes = [vp, vp]
+    L.p25o_trellis_34_decode.argtypes = [vp, vp]
     L.p25o_imbe_decode.argtypes = [vp, vp, vp]
     L.p25o_crc_ccitt.restype = C.c_uint32
     L.p25o_crc_ccitt.argtypes = [vp, C.c_int]

@@ -23,8 +23,9 @@ assert EVENT_DTYPE.itemsize == 80
 
 # names every build must export (checked by tests/test_abi.py against include/p25cu.h)
 EXPORTS = ["p25cu_create", "p25cu_destroy", "p25cu_last_error", "p25cu_demod", "p25cu_decode", "p25cu_process",
-           "p25cu_poll", "p25cu_poll_view", "p25cu_pending", "p25cu_resync", "p25cu_get_stats", "p25cu_cuda_stream", "p25cu_sync", "p25cu_set_overlap",
-           "p25cu_launch_count", "p25cu_demod_timing", "p25cu_device_baseband", "p25cu_channelizer_output", "p25cu_fec_selftest"]
+           "p25cu_poll", "p25cu_poll_view", "p25cu_pending", "p25cu_poll_start", "p25cu_poll_packed", "p25cu_unpack_events",
+           "p25cu_host_alloc", "p25cu_host_free", "p25cu_host_register", "p25cu_host_unregister", "p25cu_resync", "p25cu_get_stats", "p25cu_cuda_stream", "p25cu_sync", "p25cu_set_overlap",
+           "p25cu_launch_count", "p25cu_demod_timing", "p25cu_device_baseband", "p25cu_read_baseband", "p25cu_channelizer_output", "p25cu_fec_selftest"]
 
 
 class Config(C.Structure):
@@ -73,6 +74,13 @@ def lib() -> C.CDLL:
     L.p25cu_poll.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.p25cu_poll_view.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     L.p25cu_pending.argtypes = [vp, C.POINTER(sz)]
+    L.p25cu_poll_start.argtypes = [vp]
+    L.p25cu_poll_packed.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz), C.POINTER(i)]
+    L.p25cu_unpack_events.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]
+    L.p25cu_host_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.p25cu_host_free.argtypes = [vp, vp]
+    L.p25cu_host_register.argtypes = [vp, vp, sz]
+    L.p25cu_host_unregister.argtypes = [vp, vp]
     L.p25cu_resync.argtypes = [vp, C.c_uint32]
     L.p25cu_get_stats.argtypes = [vp, C.c_uint32, C.POINTER(Stats), i]
     L.p25cu_cuda_stream.argtypes = [vp]
@@ -83,6 +91,7 @@ def lib() -> C.CDLL:
     L.p25cu_launch_count.restype = C.c_uint64
     L.p25cu_demod_timing.argtypes = [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_uint)]
     L.p25cu_device_baseband.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
+    L.p25cu_read_baseband.argtypes = [vp, C.c_uint32, vp, sz]
     L.p25cu_channelizer_output.argtypes = [vp, vp, C.POINTER(sz)]
     L.p25cu_fec_selftest.argtypes = [vp, i, vp, sz, i, i, vp, vp]
     _lib = L

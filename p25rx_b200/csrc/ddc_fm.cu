@@ -342,8 +342,24 @@ constexpr int ACOLS = 5 * MB;
 constexpr int HC = P25_TAPS_CHAN - 1;   // channel filter history (40)
 constexpr int HB = P25_BOXCAR - 1;      // boxcar history (9)
 
+// Per-format constants of the stream kernel.  cf32 blocks start on a 16-byte boundary by construction (even a0); u8
+// blocks (2 bytes per sample, 8 samples per 16 bytes) are staged from the enclosing aligned group and read with a skew.
+template <int FMT>
+struct F {
+    static constexpr bool U8 = FMT == P25CU_FMT_U8_IQ;
+    static constexpr int ES = U8 ? 2 : 8;                       // bytes per sample
+    static constexpr int AL = U8 ? 8 : 2;                       // samples per 16 bytes
+    static constexpr int XLEN = U8 ? XN + AL : XN;              // staged samples per block
+    static constexpr int XBYTES = (XLEN * ES + 127) / 128 * 128;
+#ifndef DDC50_MAXREG
+#define DDC50_MAXREG 56
+#endif
+    static constexpr int MAXREG = U8 ? 64 : DDC50_MAXREG;
+};
+
+template <int FMT>
 struct __align__(128) Smem {
-    float2 xs[2][XN];              // TMA destinations
+    unsigned char xs[2][F<FMT>::XBYTES];   // TMA destinations (raw samples of the stream's format)
     float2 pa[4][ACOLS + 4];       // front partials q=1..4; slots 0..3 carry the previous block's last columns
     float2 ya[ACOLS];
     float2 pd[4][MB + 4];
@@ -386,6 +402,33 @@ __device__ __forceinline__ float2 cfma(float h, float2 x, float2 acc) {
           "l"(*reinterpret_cast<const unsigned long long*>(&acc)));
     return *reinterpret_cast<float2*>(&r);
 }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+
+// NS u8 samples starting at half-word ODD of wp[0] -> floats in byte units centred on 128 (PRMT builds the float
+// 2^23 + b in place, one packed add removes 2^23 + 128): 2 PRMT + 1 FADD2 per sample, no table, no I2F
+template <int NS, bool ODD>
+__device__ __forceinline__ void load_u8n(const unsigned* __restrict__ wp, float2 (&x)[NS]) {
+    constexpr int NWORD = (NS + (ODD ? 1 : 0) + 1) / 2;
+    unsigned w[NWORD];
+#pragma unroll
+    for (int i = 0; i < NWORD; i++) w[i] = wp[i];
+    const float2 off = make_float2(-8388736.f, -8388736.f);   // -(2^23 + 128)
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        const int hw = i + (ODD ? 1 : 0);
+        const unsigned word = w[hw >> 1];
+        // bytes {b, 0, 0, 0x4B}: the float 2^23 + b
+        const unsigned fi = __byte_perm(word, 0x4B000000u, (hw & 1) ? 0x7442u : 0x7440u);
+        const unsigned fq = __byte_perm(word, 0x4B000000u, (hw & 1) ? 0x7443u : 0x7441u);
+        x[i] = add2(make_float2(__uint_as_float(fi), __uint_as_float(fq)), off);
+    }
+}
 
 template <int D>
 __device__ __forceinline__ void partials(const float2 (&x)[D], const float* __restrict__ h, float2 (&P)[5]) {
@@ -398,19 +441,23 @@ __device__ __forceinline__ void partials(const float2 (&x)[D], const float* __re
     }
 }
 
-// issue the bulk copies of logical samples [l0, l0 + XN) (clipped to the data that exists) into xs[stage]
-__device__ __forceinline__ void issue_block(Smem& sm, int stage, const DdcParams& p, const float2* tail, const float2* chunk,
-                                            long long l0) {
+// issue the bulk copies of logical samples [l0, l0 + XN) (u8: from the enclosing 16-byte group on; clipped to the
+// data that exists) into xs[stage]
+template <int FMT>
+__device__ __forceinline__ void issue_block(Smem<FMT>& sm, int stage, const DdcParams& p, const unsigned char* tail,
+                                            const unsigned char* chunk, long long l0) {
+    constexpr int ES = F<FMT>::ES;
     const long long ht = p.ht, lend = ht + (long long)p.n;
-    long long l1 = l0 + XN;
+    const long long la = l0 & ~(long long)(F<FMT>::AL - 1);
+    long long l1 = la + F<FMT>::XLEN;
     if (l1 > lend) l1 = lend;
     const long long t1 = l1 < ht ? l1 : ht;       // end of the part served by the tail
-    const unsigned nt = l0 < t1 ? (unsigned)(t1 - l0) : 0u;
-    const long long cb = l0 > ht ? l0 : ht;       // start of the part served by the chunk
+    const unsigned nt = la < t1 ? (unsigned)(t1 - la) : 0u;
+    const long long cb = la > ht ? la : ht;       // start of the part served by the chunk
     const unsigned nc = cb < l1 ? (unsigned)(l1 - cb) : 0u;
-    mbar_expect_tx(&sm.full[stage], (nt + nc) * 8u);
-    if (nt) tma_load_1d(&sm.xs[stage][0], tail + l0, nt * 8u, &sm.full[stage]);
-    if (nc) tma_load_1d(&sm.xs[stage][cb - l0], chunk + (cb - ht), nc * 8u, &sm.full[stage]);
+    mbar_expect_tx(&sm.full[stage], (nt + nc) * ES);
+    if (nt) tma_load_1d(&sm.xs[stage][0], tail + la * ES, nt * ES, &sm.full[stage]);
+    if (nc) tma_load_1d(&sm.xs[stage][(cb - la) * ES], chunk + (cb - ht) * ES, nc * ES, &sm.full[stage]);
 }
 
 // Work distribution: the flattened (stream, block) space is split into a static part (n_static consecutive blocks per
@@ -426,14 +473,16 @@ __device__ __forceinline__ void issue_block(Smem& sm, int stage, const DdcParams
 #endif
 constexpr unsigned DYN_CH = DDC50_DYN_CH;
 
-#ifndef DDC50_MAXREG
-#define DDC50_MAXREG 56
-#endif
-__global__ void __maxnreg__(DDC50_MAXREG) p25_ddc_fm_stream_kernel(const DdcParams p, const unsigned blocks_per_stream,
-                                                                  const unsigned n_static, const unsigned n_tickets,
-                                                                  const unsigned ticket_base) {
+// u8 input (declared extension: the reference's sample format at the 2.4 MS/s rate): samples stay in byte units
+// centred on 128 like in the /5 kernels below; `dc` restores the half-LSB offset after the (unit-DC-gain) filters,
+// `pw_scale` rescales the power.  For cf32 dc = 0 and pw_scale = 1.
+template <int FMT>
+__global__ void __maxnreg__(F<FMT>::MAXREG) p25_ddc_fm_stream_kernel(const DdcParams p, const unsigned blocks_per_stream,
+                                                                    const unsigned n_static, const unsigned n_tickets,
+                                                                    const unsigned ticket_base, const float dc, const float pw_scale) {
+    constexpr int ES = F<FMT>::ES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    Smem<FMT>& sm = *reinterpret_cast<Smem<FMT>*>(smem_raw);
     __shared__ unsigned s_ticket;
     const int tid = threadIdx.x;
 
@@ -466,8 +515,8 @@ __global__ void __maxnreg__(DDC50_MAXREG) p25_ddc_fm_stream_kernel(const DdcPara
         unsigned it1 = blocks_per_stream;
         if (b_end - b < (unsigned long long)(it1 - it0)) it1 = it0 + (unsigned)(b_end - b);
         b += it1 - it0;
-        const float2* tail = (const float2*)p.tail_in + (size_t)s * p.ht;
-        const float2* chunk = (const float2*)p.iq + (size_t)s * p.n;
+        const unsigned char* tail = (const unsigned char*)p.tail_in + (size_t)s * p.ht * ES;
+        const unsigned char* chunk = (const unsigned char*)p.iq + (size_t)s * p.n * ES;
         const long long mb = M0 + (long long)it0 * MB;
         long long me = M0 + (long long)it1 * MB;
         if (me > M0 + (long long)p.n_out) me = M0 + p.n_out;
@@ -486,8 +535,8 @@ __global__ void __maxnreg__(DDC50_MAXREG) p25_ddc_fm_stream_kernel(const DdcPara
         const long long m_first = mb - MB;
         const int nblk = (int)((me - m_first + MB - 1) / MB);
         if (tid == 0) {
-            issue_block(sm, use & 1, p, tail, chunk, 50 * m_first + lbase);
-            if (nblk > 1) issue_block(sm, (use + 1) & 1, p, tail, chunk, 50 * (m_first + MB) + lbase);
+            issue_block<FMT>(sm, use & 1, p, tail, chunk, 50 * m_first + lbase);
+            if (nblk > 1) issue_block<FMT>(sm, (use + 1) & 1, p, tail, chunk, 50 * (m_first + MB) + lbase);
         }
         __syncthreads();
 
@@ -500,19 +549,26 @@ __global__ void __maxnreg__(DDC50_MAXREG) p25_ddc_fm_stream_kernel(const DdcPara
             float2 P[5];
             {
                 float2 x[10];
-                const float4* src = reinterpret_cast<const float4*>(&sm.xs[stage][10 * tid]);
+                if constexpr (F<FMT>::U8) {
+                    const int s0 = (int)((50 * mi + lbase) & (F<FMT>::AL - 1)) + 10 * tid;   // skew inside the staged group
+                    const unsigned* wp = reinterpret_cast<const unsigned*>(sm.xs[stage]) + (s0 >> 1);
+                    if (s0 & 1) load_u8n<10, true>(wp, x);
+                    else load_u8n<10, false>(wp, x);
+                } else {
+                    const float4* src = reinterpret_cast<const float4*>(sm.xs[stage]) + 5 * tid;
 #pragma unroll
-                for (int i = 0; i < 5; i++) {
-                    const float4 v = src[i];
-                    x[2 * i] = make_float2(v.x, v.y);
-                    x[2 * i + 1] = make_float2(v.z, v.w);
+                    for (int i = 0; i < 5; i++) {
+                        const float4 v = src[i];
+                        x[2 * i] = make_float2(v.x, v.y);
+                        x[2 * i + 1] = make_float2(v.z, v.w);
+                    }
                 }
                 partials<10>(x, c_taps_front, P);
             }
 #pragma unroll
             for (int q = 1; q < 5; q++) sm.pa[q - 1][tid + 4] = P[q];
             __syncthreads();                                                  // B1: xs[stage] fully consumed
-            if (tid == 0 && blk + 2 < nblk) issue_block(sm, stage, p, tail, chunk, 50 * (mi + 2 * MB) + lbase);
+            if (tid == 0 && blk + 2 < nblk) issue_block<FMT>(sm, stage, p, tail, chunk, 50 * (mi + 2 * MB) + lbase);
             {
                 float2 a = P[0];
 #pragma unroll
@@ -556,7 +612,7 @@ __global__ void __maxnreg__(DDC50_MAXREG) p25_ddc_fm_stream_kernel(const DdcPara
             }
             // channel FIR at 48 kHz (two accumulators for ILP)
             if (tid < MB) {
-                float2 e = make_float2(0.f, 0.f), o = make_float2(0.f, 0.f);
+                float2 e = make_float2(dc, dc), o = make_float2(0.f, 0.f);
                 const float2* src = &sm.yd[HC + tid];
 #pragma unroll
                 for (int k = 0; k + 1 < P25_TAPS_CHAN; k += 2) {
@@ -599,13 +655,14 @@ __global__ void __maxnreg__(DDC50_MAXREG) p25_ddc_fm_stream_kernel(const DdcPara
             if (tid == 0) {
                 float t = 0.f;
                 for (int i = 0; i < NT / 32; i++) t += sm.red[i];
-                atomicAdd(p.power_sum + s, t);
+                atomicAdd(p.power_sum + s, t * pw_scale);
             }
         }
         if (it1 == blocks_per_stream) {   // this piece ends the stream's chunk: write the tail for the next chunk
-            float2* tout = (float2*)p.tail_out + (size_t)s * p.ht;
+            using ET = typename Elem<FMT>::T;
+            ET* tout = (ET*)p.tail_out + (size_t)s * p.ht;
             for (int i = tid; i < (int)p.ht; i += NT)
-                tout[i] = load_logical_raw<P25CU_FMT_CF32_IQ>(p, tail, chunk, (long long)p.n + i);
+                tout[i] = load_logical_raw<FMT>(p, tail, chunk, (long long)p.n + i);
         }
         __syncthreads();
     }
@@ -671,13 +728,7 @@ struct __align__(128) Smem {
     unsigned long long full[2];
 };
 
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;"
-        : "=l"(r)
-        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
-    return *reinterpret_cast<float2*>(&r);
-}
+using fast::add2;
 
 // atan2 for the discriminator: |error| <= 2e-7 rad (degree-7 minimax in t^2 on [0, 1], spec/gen_tables.py
 // style fit; CUDA's atan2f costs ~85 instructions with its special-case branches, this one ~22, branch-free).
@@ -746,20 +797,7 @@ __device__ __forceinline__ float2 disc_atan2_pair(float2 y, float2 x) {
 // 5R u8 samples starting at half-word ODD of wp[0] -> floats in byte units centred on 128
 template <int R, bool ODD>
 __device__ __forceinline__ void load_u8(const unsigned* __restrict__ wp, float2 (&x)[5 * R]) {
-    constexpr int NWORD = (5 * R + (ODD ? 1 : 0) + 1) / 2;
-    unsigned w[NWORD];
-#pragma unroll
-    for (int i = 0; i < NWORD; i++) w[i] = wp[i];
-    const float2 off = make_float2(-8388736.f, -8388736.f);   // -(2^23 + 128)
-#pragma unroll
-    for (int i = 0; i < 5 * R; i++) {
-        const int hw = i + (ODD ? 1 : 0);
-        const unsigned word = w[hw >> 1];
-        // bytes {b, 0, 0, 0x4B}: the float 2^23 + b
-        const unsigned fi = __byte_perm(word, 0x4B000000u, (hw & 1) ? 0x7442u : 0x7440u);
-        const unsigned fq = __byte_perm(word, 0x4B000000u, (hw & 1) ? 0x7443u : 0x7441u);
-        x[i] = add2(make_float2(__uint_as_float(fi), __uint_as_float(fq)), off);
-    }
+    fast::load_u8n<5 * R, ODD>(wp, x);
 }
 
 // bulk copies of logical samples [l0 - skew, ...) covering the tile's window into xs[stage]
@@ -1239,38 +1277,39 @@ template <bool FRONT, int FMT>
 static cudaError_t launch(const DdcParams& p, cudaStream_t st) {
     using C = Cfg<FRONT>;
     auto kern = p25_ddc_fm_kernel<FRONT, FMT>;
-    const size_t smem = sizeof(Smem<FRONT>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    const size_t smem = sizeof(Smem<FRONT>);   // opted in per device by p25cu_ddc_plan_device
     kern<<<p.n_streams * p.n_seg, C::NT, smem, st>>>(p);
     return cudaGetLastError();
 }
 
 unsigned p25cu_ddc_block_out(int decimation) { return decimation == 50 ? Cfg<true>::MB : Cfg<false>::MB; }
 
+// DC gain of a tap set (double): u8 samples run through the fast kernels in byte units centred on 128,
+// x_true = (u - 128 + 0.5) / 127.5 (spec iq_lut), so the half LSB reappears after the filters as 0.5 * (product of gains)
+static double tap_gain(const float* h, int n) {
+    double g = 0.0;
+    for (int k = 0; k < n; k++) g += (double)h[k];
+    return g;
+}
+
+template <int FMT>
 static cudaError_t launch_fast(const DdcParams& p, cudaStream_t st) {
-    static int grid_cache = 0;
-    const size_t smem = sizeof(fast::Smem);
-    if (!grid_cache) {
-        cudaError_t e = cudaFuncSetAttribute(fast::p25_ddc_fm_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int dev = 0, n_sm = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast::p25_ddc_fm_stream_kernel, fast::NT, smem);
-        if (e != cudaSuccess) return e;
-        if (const char* ev = getenv("P25CU_DDC_CTAS")) per_sm = atoi(ev);   // A/B: CTAs per SM of the persistent grid
-        grid_cache = n_sm * (per_sm > 0 ? per_sm : 1);
-    }
+    constexpr bool U8 = FMT == P25CU_FMT_U8_IQ;
+    const size_t smem = sizeof(fast::Smem<FMT>);
+    const int grid_max = U8 ? p.plan->grid_ddc50_u8 : p.plan->grid_ddc50;
     const unsigned bps = (p.n_out + fast::MB - 1) / fast::MB;
     const unsigned long long total = (unsigned long long)p.n_streams * bps;
-    const unsigned grid = total < (unsigned long long)grid_cache ? (unsigned)total : (unsigned)grid_cache;
+    const unsigned grid = total < (unsigned long long)grid_max ? (unsigned)total : (unsigned)grid_max;
     // 7/8 of the blocks are split statically, the rest goes out in tickets; the ticket counter only ever grows, every
     // launch consumes n_tickets + grid draws (each CTA stops at its first out-of-range ticket)
     const unsigned n_static = (unsigned)(total / grid * DDC50_STATIC_NUM / DDC50_STATIC_DEN);
     const unsigned long long dyn = total - (unsigned long long)n_static * grid;
     const unsigned n_tickets = (unsigned)((dyn + fast::DYN_CH - 1) / fast::DYN_CH);
-    fast::p25_ddc_fm_stream_kernel<<<grid, fast::NT, smem, st>>>(p, bps, n_static, n_tickets, *p.ticket_base);
+    const float dc = U8 ? (float)(0.5 * tap_gain(P25_TAPS_FRONT_H, P25_TAPS_FRONT) * tap_gain(P25_TAPS_DECIM_H, P25_TAPS_DECIM) *
+                                  tap_gain(P25_TAPS_CHAN_H, P25_TAPS_CHAN))
+                        : 0.f;
+    const float pw_scale = U8 ? (float)(1.0 / (127.5 * 127.5)) : 1.f;
+    fast::p25_ddc_fm_stream_kernel<FMT><<<grid, fast::NT, smem, st>>>(p, bps, n_static, n_tickets, *p.ticket_base, dc, pw_scale);
     *p.ticket_base += n_tickets + grid;
     return cudaGetLastError();
 }
@@ -1278,27 +1317,13 @@ static cudaError_t launch_fast(const DdcParams& p, cudaStream_t st) {
 template <int FMT>
 static cudaError_t launch_fast5(const DdcParams& p, cudaStream_t st) {
     using C = fast5::K<FMT>;
-    static int grid_cache = 0;
     auto kern = fast5::p25_ddc5_fm_kernel<FMT>;
     const size_t smem = sizeof(fast5::Smem<FMT>);
-    if (!grid_cache) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int dev = 0, n_sm = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NT, smem);
-        if (e != cudaSuccess) return e;
-        grid_cache = n_sm * (per_sm > 0 ? per_sm : 1);
-    }
+    const int grid_max = p.plan->grid_fast5[FMT];
     const unsigned tps = (p.n_out + C::MB - 1) / C::MB;
     const unsigned long long total = (unsigned long long)p.n_streams * tps;
-    const unsigned grid = total < (unsigned long long)grid_cache ? (unsigned)total : (unsigned)grid_cache;
-    // u8 samples are processed in byte units centred on 128: x_true = (u + 0.5) / 127.5 (spec iq_lut)
-    double gd = 0.0, gc = 0.0;
-    for (int k = 0; k < P25_TAPS_DECIM; k++) gd += (double)P25_TAPS_DECIM_H[k];
-    for (int k = 0; k < P25_TAPS_CHAN; k++) gc += (double)P25_TAPS_CHAN_H[k];
-    const float dc = C::U8 ? (float)(0.5 * gd * gc) : 0.f;
+    const unsigned grid = total < (unsigned long long)grid_max ? (unsigned)total : (unsigned)grid_max;
+    const float dc = C::U8 ? (float)(0.5 * tap_gain(P25_TAPS_DECIM_H, P25_TAPS_DECIM) * tap_gain(P25_TAPS_CHAN_H, P25_TAPS_CHAN)) : 0.f;
     const float pw_scale = C::U8 ? (float)(1.0 / (127.5 * 127.5)) : 1.f;
     kern<<<grid, C::NT, smem, st>>>(p, tps, dc, pw_scale);
     return cudaGetLastError();
@@ -1306,30 +1331,52 @@ static cudaError_t launch_fast5(const DdcParams& p, cudaStream_t st) {
 
 template <int FMT>
 static cudaError_t launch_w5(const DdcParams& p, cudaStream_t st) {
-    static int grid_cache = 0;
     auto kern = w5::p25_ddc5_warp_kernel<FMT>;
     const size_t smem = sizeof(w5::WarpSm<FMT>) * w5::WARPS;
-    if (!grid_cache) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int dev = 0, n_sm = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * w5::WARPS, smem);
-        if (e != cudaSuccess) return e;
-        grid_cache = n_sm * (per_sm > 0 ? per_sm : 1);
-    }
+    const int grid_max = p.plan->grid_w5[FMT];
     const unsigned ips = (p.n_out + w5::NOUT - 1) / w5::NOUT;
     const unsigned long long total = (unsigned long long)p.n_streams * ips;
     unsigned long long want = (total + 3) / 4;                 // at least ~4 iterations per warp (one warm-up each)
     want = (want + w5::WARPS - 1) / w5::WARPS;
-    const unsigned grid = want < (unsigned long long)grid_cache ? (unsigned)(want ? want : 1) : (unsigned)grid_cache;
-    double gd = 0.0, gc = 0.0;
-    for (int k = 0; k < P25_TAPS_DECIM; k++) gd += (double)P25_TAPS_DECIM_H[k];
-    for (int k = 0; k < P25_TAPS_CHAN; k++) gc += (double)P25_TAPS_CHAN_H[k];
+    const unsigned grid = want < (unsigned long long)grid_max ? (unsigned)(want ? want : 1) : (unsigned)grid_max;
     const bool u8 = FMT == P25CU_FMT_U8_IQ;
-    kern<<<grid, 32 * w5::WARPS, smem, st>>>(p, ips, u8 ? (float)(0.5 * gd * gc) : 0.f, u8 ? (float)(1.0 / (127.5 * 127.5)) : 1.f);
+    const float dc = u8 ? (float)(0.5 * tap_gain(P25_TAPS_DECIM_H, P25_TAPS_DECIM) * tap_gain(P25_TAPS_CHAN_H, P25_TAPS_CHAN)) : 0.f;
+    kern<<<grid, 32 * w5::WARPS, smem, st>>>(p, ips, dc, u8 ? (float)(1.0 / (127.5 * 127.5)) : 1.f);
     return cudaGetLastError();
+}
+
+// Per-device setup (called once per device under the library's plan mutex, with that device current): opt every
+// kernel into its dynamic shared memory and size the persistent grids from the device's own occupancy.
+template <typename K>
+static cudaError_t plan_one(K kern, int threads, size_t smem, int n_sm, int* grid) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    *grid = n_sm * (per_sm > 0 ? per_sm : 1);
+    return cudaSuccess;
+}
+
+cudaError_t p25cu_ddc_plan_device(P25DevPlan* plan) {
+    cudaError_t e;
+    const int n_sm = plan->n_sm;
+    constexpr int U8 = P25CU_FMT_U8_IQ, CF = P25CU_FMT_CF32_IQ;
+    if ((e = plan_one(fast::p25_ddc_fm_stream_kernel<CF>, fast::NT, sizeof(fast::Smem<CF>), n_sm, &plan->grid_ddc50)) != cudaSuccess) return e;
+    if ((e = plan_one(fast::p25_ddc_fm_stream_kernel<U8>, fast::NT, sizeof(fast::Smem<U8>), n_sm, &plan->grid_ddc50_u8)) != cudaSuccess) return e;
+    if (const char* ev = getenv("P25CU_DDC_CTAS")) {   // A/B: CTAs per SM of the persistent /50 grids
+        const int per_sm = atoi(ev);
+        if (per_sm > 0) plan->grid_ddc50 = plan->grid_ddc50_u8 = n_sm * per_sm;
+    }
+    if ((e = plan_one(fast5::p25_ddc5_fm_kernel<U8>, fast5::K<U8>::NT, sizeof(fast5::Smem<U8>), n_sm, &plan->grid_fast5[U8])) != cudaSuccess) return e;
+    if ((e = plan_one(fast5::p25_ddc5_fm_kernel<CF>, fast5::K<CF>::NT, sizeof(fast5::Smem<CF>), n_sm, &plan->grid_fast5[CF])) != cudaSuccess) return e;
+    if ((e = plan_one(w5::p25_ddc5_warp_kernel<U8>, 32 * w5::WARPS, sizeof(w5::WarpSm<U8>) * w5::WARPS, n_sm, &plan->grid_w5[U8])) != cudaSuccess) return e;
+    if ((e = plan_one(w5::p25_ddc5_warp_kernel<CF>, 32 * w5::WARPS, sizeof(w5::WarpSm<CF>) * w5::WARPS, n_sm, &plan->grid_w5[CF])) != cudaSuccess) return e;
+    // the generic kernels' shared memory (27 - 72 KB) needs the opt-in as well
+    if ((e = cudaFuncSetAttribute(p25_ddc_fm_kernel<true, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<true>))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(p25_ddc_fm_kernel<true, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<true>))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(p25_ddc_fm_kernel<false, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<false>))) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(p25_ddc_fm_kernel<false, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<false>));
 }
 
 // /5 fast paths: bit 0 = warp-autonomous kernel for u8, bit 1 = for cf32 (otherwise the tile kernel); A/B switch P25CU_DDC5
@@ -1349,7 +1396,11 @@ cudaError_t p25cu_launch_ddc(const DdcParams& p, int format, int decimation, cud
         return format == P25CU_FMT_CF32_IQ ? launch_fast5<P25CU_FMT_CF32_IQ>(p, st) : launch_fast5<P25CU_FMT_U8_IQ>(p, st);
     if (decimation == 50 && format == P25CU_FMT_CF32_IQ && p.aligned16 && (p.a0 & 1ull) == 0 && p.n_out > 0 &&
         p.ht == (unsigned)Cfg<true>::HT)
-        return launch_fast(p, st);
+        return launch_fast<P25CU_FMT_CF32_IQ>(p, st);
+    // u8 at 2.4 MS/s: any decimator phase (blocks are staged from their enclosing 16-byte group); like the /5 fast paths the
+    // whole history must lie inside the stream (no byte encodes the zeros in front of a stream start)
+    if (decimation == 50 && format == P25CU_FMT_U8_IQ && p.aligned16 && p.n_out > 0 && p.a0 >= p.ht && p.ht == (unsigned)Cfg<true>::HT)
+        return launch_fast<P25CU_FMT_U8_IQ>(p, st);
     if (decimation == 50)
         return format == P25CU_FMT_CF32_IQ ? launch<true, P25CU_FMT_CF32_IQ>(p, st) : launch<true, P25CU_FMT_U8_IQ>(p, st);
     return format == P25CU_FMT_CF32_IQ ? launch<false, P25CU_FMT_CF32_IQ>(p, st) : launch<false, P25CU_FMT_U8_IQ>(p, st);

@@ -25,6 +25,8 @@
 // so events and their sample indices are bit-identical for any chunking.  This file is
 // compiled with --fmad=false: the only fused operations are the explicit fmaf() of the
 // correlator, in the same order as the oracle.
+#include <mutex>
+
 #include "p25cu_internal.cuh"
 
 #define FULL 0xFFFFFFFFu
@@ -46,6 +48,7 @@ struct WalkShared {
     alignas(16) float win[P25CU_WALK_WARPS][2 * WIN_PAD];    // the search window twice: [0, WIN_PAD) and shifted by one sample
     PendingEvent pend[P25CU_WALK_WARPS];
     alignas(16) unsigned char scr[P25CU_WALK_WARPS][192];   // decoder work area (syndromes, locator, IMBE results)
+    unsigned surv[P25CU_WALK_WARPS][52];        // 3/4-rate trellis survivors: 8 states x 3 bits per step
     unsigned short pn_a[116], pn_c[116];        // IMBE PN generator n steps ahead: p_n = pn_a[n] * p_0 + pn_c[n] (mod 2^16)
     unsigned char imbe_src[8 * 24];             // inverse of the IMBE interleave schedule: [code word][bit] -> frame bit
 };
@@ -74,12 +77,12 @@ struct WarpCtx {
 
 // ---------------------------------------------------------------- lane-0 helpers
 __device__ __forceinline__ void stat_ok(const WarpCtx& c, int fam, unsigned fixed) {
-    unsigned* s = c.p->stats + ((size_t)c.stream * P25CU_ST_FAMILIES + fam) * 3;
+    unsigned long long* s = c.p->stats + ((size_t)c.stream * P25CU_ST_FAMILIES + fam) * 3;
     s[0] += 1;
     s[2] += fixed;
 }
 __device__ __forceinline__ void stat_bad(const WarpCtx& c, int fam) {
-    unsigned* s = c.p->stats + ((size_t)c.stream * P25CU_ST_FAMILIES + fam) * 3;
+    unsigned long long* s = c.p->stats + ((size_t)c.stream * P25CU_ST_FAMILIES + fam) * 3;
     s[0] += 1;
     s[1] += 1;
 }
@@ -100,28 +103,28 @@ __device__ __forceinline__ void emit(const WarpCtx& c, unsigned kind, unsigned l
     c.pend->valid = 1;
 }
 
-// whole warp: one 80-byte event record = 20 words, one per lane (payload bytes beyond len are zero)
+// whole warp: one packed record = 3 header words + ceil(len / 4) payload words, one word per lane
+// (word 0 stream, word 1 sample bits 0..31, word 2 sample bits 32..47 | kind << 16 | len << 24)
 __device__ __forceinline__ void flush_event(const WarpCtx& c, int lane) {
     if (!c.pend->valid) return;
     WalkState& ws = *c.ws;
-    const unsigned len = c.pend->len;
+    const unsigned len = c.pend->len, nw = p25cu_packed_words(len);
     unsigned w = 0;
     if (lane == 0) w = c.stream;
-    else if (lane == 1) w = c.pend->kind;
-    else if (lane == 2) w = (unsigned)c.pend->idx;
-    else if (lane == 3) w = (unsigned)(c.pend->idx >> 32);
-    else if (lane == 4) w = len;
-    else if (lane < 20) {
-        const unsigned b0 = 4 * (lane - 5);
+    else if (lane == 1) w = (unsigned)c.pend->idx;
+    else if (lane == 2) w = ((unsigned)(c.pend->idx >> 32) & 0xFFFFu) | (c.pend->kind << 16) | (len << 24);
+    else if (lane < (int)nw) {
+        const unsigned b0 = 4 * (lane - 3);
 #pragma unroll
         for (int i = 0; i < 4; i++)
             if (b0 + i < len) w |= (unsigned)c.payload[b0 + i] << (8 * i);
     }
-    unsigned* dst = (unsigned*)(c.p->slots + (size_t)c.stream * c.p->ev_cap + ws.n_events);
-    if (lane < 20) dst[lane] = w;
+    unsigned* dst = c.p->slots + (size_t)c.stream * c.p->ev_cap * P25CU_SLOT_WORDS + ws.n_words;
+    if (lane < (int)nw) dst[lane] = w;
     __syncwarp();
     if (lane == 0) {
         ws.n_events++;
+        ws.n_words += nw;
         c.pend->valid = 0;
     }
     __syncwarp();
@@ -153,13 +156,11 @@ __device__ __forceinline__ void nid_apply(const WarpCtx& c, unsigned long long i
     ws.cnt = ws.blocks = ws.part = ws.chunks = 0;
     switch (ws.duid) {
         case 0x0: case 0x5: case 0xA: case 0xF: case 0x7:
+        case 0xC:   // packet data: header block + the data blocks it announces (stats and errors only, no MessageEvent)
             ws.state = WS_PAYLOAD;
             break;
         case 0x3:
             ws.state = WS_FLUSH;
-            break;
-        case 0xC:
-            enter_sync(ws, idx + 1);
             break;
         default:
             fail(c, P25CU_E_UNKNOWN_NID, idx);
@@ -299,6 +300,63 @@ __device__ __noinline__ int warp_trellis_half_decode(const P25DevTables& T, unsi
         for (int i = 48; i >= 0; i--) {
             if (i < 48) out12[i >> 2] |= (unsigned char)(st << (6 - 2 * (i & 3)));
             st = (scratch[i] >> (2 * st)) & 3;
+        }
+    }
+    __syncwarp();
+    return m0;
+}
+
+// 3/4-rate trellis (confirmed packet data), all 32 lanes: lane = (next state, two previous states pa and pa + 4);
+// add-compare-select on the key (path metric << 3 | previous state) -- own pair, then two shuffle steps -- which keeps
+// the lowest predecessor on ties exactly like p25_trellis_34_decode.  Survivors: 8 x 3 bits per step in surv[], traced
+// back by lane 0.
+__device__ __noinline__ int warp_trellis_34_decode(const P25DevTables& T, unsigned* surv, const unsigned char* dibits, int lane,
+                                                   unsigned char* out18) {
+    int s0 = 0, s1 = 0;
+    {
+        const int slot = T.interleave[lane];
+        s0 = (dibits[2 * slot] << 2) | dibits[2 * slot + 1];
+        if (lane + 32 < 49) {
+            const int slot1 = T.interleave[lane + 32];
+            s1 = (dibits[2 * slot1] << 2) | dibits[2 * slot1 + 1];
+        }
+    }
+    const int ns = lane >> 2, pa = lane & 3, pb = pa + 4;
+    const int ea = T.trellis34_pair[8 * pa + ns], eb = T.trellis34_pair[8 * pb + ns];
+    int ma = pa == 0 ? 0 : (1 << 20), mb = 1 << 20;   // metrics of states pa and pb as seen by this lane
+#pragma unroll 1
+    for (int i = 0; i < 49; i++) {
+        const int sym = __shfl_sync(FULL, i < 32 ? s0 : s1, i & 31);
+        const int ka = ((ma + __popc(ea ^ sym)) << 3) | pa, kb = ((mb + __popc(eb ^ sym)) << 3) | pb;
+        int key = min(ka, kb);
+        key = min(key, __shfl_xor_sync(FULL, key, 1));
+        key = min(key, __shfl_xor_sync(FULL, key, 2));
+        const unsigned b0 = __ballot_sync(FULL, key & 1), b1 = __ballot_sync(FULL, key & 2), b2 = __ballot_sync(FULL, key & 4);
+        if (lane == 0) {
+            unsigned f = 0;
+#pragma unroll
+            for (int g = 0; g < 8; g++)
+                f |= (((b0 >> (4 * g)) & 1u) | (((b1 >> (4 * g)) & 1u) << 1) | (((b2 >> (4 * g)) & 1u) << 2)) << (3 * g);
+            surv[i] = f;
+        }
+        const int nm = key >> 3;                        // new metric of state ns, held by group ns
+        ma = __shfl_sync(FULL, nm, 4 * pa);
+        mb = __shfl_sync(FULL, nm, 4 * pb);
+    }
+    const int m0 = __shfl_sync(FULL, ma, 0);            // lane 0 has pa = 0
+    __syncwarp();
+    if (m0 > P25_VITERBI34_MAX_FIX) return -1;
+    if (lane == 0) {
+        for (int i = 0; i < P25_PDU_BLOCK34_BYTES; i++) out18[i] = 0;
+        int st = 0;
+        for (int i = 48; i >= 0; i--) {
+            if (i < 48) {
+                for (int b = 0; b < 3; b++) {
+                    const int bit = 3 * i + b;
+                    out18[bit >> 3] |= (unsigned char)(((st >> (2 - b)) & 1) << (7 - (bit & 7)));
+                }
+            }
+            st = (surv[i] >> (3 * st)) & 7;
         }
     }
     __syncwarp();
@@ -498,7 +556,7 @@ __device__ __forceinline__ void warp_pack_hexbits(const unsigned char* hex, int 
 
 // lane 0 adds a batch of code-word outcomes to a stats family (n words, `bad` of them uncorrectable, `fixed` bits)
 __device__ __forceinline__ void stat_batch(const WarpCtx& c, int fam, unsigned n, unsigned bad, unsigned fixed) {
-    unsigned* s = c.p->stats + ((size_t)c.stream * P25CU_ST_FAMILIES + fam) * 3;
+    unsigned long long* s = c.p->stats + ((size_t)c.stream * P25CU_ST_FAMILIES + fam) * 3;
     s[0] += n;
     s[1] += bad;
     s[2] += fixed;
@@ -627,6 +685,44 @@ __device__ __noinline__ void complete_payload(const WarpCtx& c, const WalkShared
     }
 }
 
+// One 98-dibit block of a packet data unit (DUID 0xC).  The header block is 1/2-rate coded and announces the number of
+// data blocks and their format; confirmed data blocks are 3/4-rate coded, unconfirmed ones 1/2-rate [STD].  No
+// MessageEvent variant carries packet data (reference src/recv.rs:214-233): only the viterbiDibit / viterbiTribit
+// stats families (src/hub.rs:569-570) and P25Error values leave the receiver.  ws.blocks = blocks decoded so far,
+// ws.part = data blocks announced, ws.chunks = confirmed format.  Called by the whole warp.
+__device__ __noinline__ void pdu_block(const WarpCtx& c, WalkShared& sh, int warp, unsigned long long idx, int lane) {
+    WalkState& ws = *c.ws;
+    unsigned char* out = c.payload;                      // 18 bytes at most
+    const bool header = ws.blocks == 0;
+    const bool tri = !header && ws.chunks;
+    int fixed;
+    if (tri) fixed = warp_trellis_34_decode(sh.T, sh.surv[warp], ws.buf, lane, out);
+    else fixed = warp_trellis_half_decode(sh.T, sh.scr[warp], ws.buf, lane, out);
+    __syncwarp();
+    if (lane == 0) {
+        ws.cnt = 0;
+        const int fam = tri ? P25CU_ST_VITERBI_TRIBIT : P25CU_ST_VITERBI_DIBIT;
+        if (fixed < 0) {
+            stat_bad(c, fam);
+            fail(c, tri ? P25CU_E_VITERBI_TRIBIT : P25CU_E_VITERBI_DIBIT, idx);
+        } else {
+            stat_ok(c, fam, (unsigned)fixed);
+            if (header) {
+                if (p25_crc_ccitt(out, 10) != (((unsigned)out[10] << 8) | out[11])) {
+                    enter_sync(ws, idx + 1);             // the length field cannot be trusted: drop lock
+                } else {
+                    ws.blocks = 1;
+                    ws.part = out[6] & 0x7F;
+                    ws.chunks = (out[0] & 0x1F) == P25_PDU_FORMAT_CONFIRMED;
+                    if (ws.part == 0) ws.state = WS_FLUSH;
+                }
+            } else if (++ws.blocks == 1 + ws.part) {
+                ws.state = WS_FLUSH;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- the walker
 // Stage the decode tables and build the derived ones (callers __syncthreads() before use).
 __device__ __forceinline__ void walk_shared_init(WalkShared& sh, const P25DevTables* tables) {
@@ -654,10 +750,24 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
     // is launched as a small persistent grid that fits beside the next chunk's demod CTAs (p25cu_launch_walk)
   for (unsigned stream = blockIdx.x * P25CU_WALK_WARPS + warp; stream < p.n_streams; stream += gridDim.x * P25CU_WALK_WARPS) {
     __syncwarp();
-    {
+    {   // header, then the dibits of the unit in flight (kept 4 per byte in HBM, one per byte here)
         const uint4* src = (const uint4*)(p.states + stream);
         uint4* dst = (uint4*)&ws;
-        for (unsigned i = lane; i < sizeof(WalkState) / 16; i += 32) dst[i] = src[i];
+        if (lane < (int)(sizeof(WalkHeader) / 16)) dst[lane] = src[lane];
+        __syncwarp();
+        const int st0 = ws.state;
+        const int held = (st0 == WS_NID || st0 == WS_PAYLOAD) ? ws.cnt : 0;
+        const unsigned* pk = p.states[stream].packed;
+        for (int j = lane; 16 * j < held; j += 32) {
+            const unsigned w = pk[j];
+            unsigned o[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const unsigned b = (w >> (8 * q)) & 0xFFu;
+                o[q] = (b & 3u) | (((b >> 2) & 3u) << 8) | (((b >> 4) & 3u) << 16) | (((b >> 6) & 3u) << 24);
+            }
+            reinterpret_cast<uint4*>(ws.buf)[j] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
     WarpCtx c{&p, &sh.T, &ws, stream, &sh.pend[warp], sh.scr[warp] + 128};
     if (lane == 0) sh.pend[warp].valid = 0;
@@ -835,7 +945,7 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
             target = P25_NID_DIBITS;
         } else if (st == WS_PAYLOAD) {
             const int duid = ws.duid;
-            if (duid == 0x7) target = P25_TSBK_DIBITS;
+            if (duid == 0x7 || duid == 0xC) target = P25_TSBK_DIBITS;
             else if (duid == 0x0) target = P25_HDU_DIBITS;
             else if (duid == 0xF) target = P25_TDULC_DIBITS;
             else target = sh.T.ldu_start[ws.part] + sh.T.ldu_len[ws.part];
@@ -898,6 +1008,8 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
                 unsigned char* out = ws.hex;   // 12-byte result area
                 const int fixed = warp_trellis_half_decode(sh.T, sh.scr[warp], ws.buf, lane, out);
                 if (lane == 0) tsbk_apply(c, idx, fixed, out);
+            } else if (ws.duid == 0xC) {
+                pdu_block(c, sh, warp, idx, lane);
             } else {
                 complete_payload(c, sh, sh.scr[warp], idx, lane);
             }
@@ -911,7 +1023,21 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
     {
         uint4* dst = (uint4*)(p.states + stream);
         const uint4* src = (const uint4*)&ws;
-        for (unsigned i = lane; i < sizeof(WalkState) / 16; i += 32) dst[i] = src[i];
+        if (lane < (int)(sizeof(WalkHeader) / 16)) dst[lane] = src[lane];
+        const int st1 = ws.state;
+        const int held = (st1 == WS_NID || st1 == WS_PAYLOAD) ? ws.cnt : 0;
+        unsigned* pk = p.states[stream].packed;
+        for (int j = lane; 16 * j < held; j += 32) {
+            const uint4 v = reinterpret_cast<const uint4*>(ws.buf)[j];
+            const unsigned in[4] = {v.x, v.y, v.z, v.w};
+            unsigned w = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const unsigned x = in[q];
+                w |= ((x & 3u) | (((x >> 8) & 3u) << 2) | (((x >> 16) & 3u) << 4) | (((x >> 24) & 3u) << 6)) << (8 * q);
+            }
+            pk[j] = w;
+        }
     }
     float* nxt = p.bb_next + (size_t)stream * p.row_stride;
     float keep[P25CU_BB_HIST / 32];
@@ -927,17 +1053,28 @@ cudaError_t p25cu_walk_upload_consts() {
     return cudaMemcpyToSymbol(c_sync_fp, P25_SYNC_FP, sizeof(float) * P25_FP_LEN);
 }
 
-cudaError_t p25cu_launch_walk(const WalkParams& p, cudaStream_t st, unsigned max_blocks) {
+cudaError_t p25cu_launch_walk(const WalkParams& p, cudaStream_t st, unsigned max_blocks, int device) {
     // Beside a demod kernel (max_blocks != 0) keep the SM's shared-memory carve-out at its maximum: that kernel needs
     // ~204 KB per SM and an SM cannot change its carve-out while any CTA is resident on it -- a walker CTA that asked
     // for the default (L1-heavy) split kept the demod CTAs off its SM until it exited (measured: 0.48 -> 0.71 ms).
     // Alone, the walker prefers the L1-heavy default (its row reads hit L1; 0.089 vs 0.104 ms).
-    static int carve_state = -2;
+    // The attribute is a per-device property of the function and contexts on several devices (or two contexts on one
+    // device with different overlap settings) may launch from different host threads: the last value set is tracked
+    // per device and the set + launch pair runs under a mutex.
+    static std::mutex mu;
+    static int carve_state[P25CU_MAX_DEVICES];
+    static bool init = false;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!init) {
+        for (int i = 0; i < P25CU_MAX_DEVICES; i++) carve_state[i] = -2;
+        init = true;
+    }
     const int want = max_blocks ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
-    if (carve_state != want) {
+    if (device < 0 || device >= P25CU_MAX_DEVICES) return cudaErrorInvalidDevice;
+    if (carve_state[device] != want) {
         cudaError_t e = cudaFuncSetAttribute(p25_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, want);
         if (e != cudaSuccess) return e;
-        carve_state = want;
+        carve_state[device] = want;
     }
     unsigned blocks = (p.n_streams + P25CU_WALK_WARPS - 1) / P25CU_WALK_WARPS;
     if (max_blocks && blocks > max_blocks) blocks = max_blocks;   // persistent: one small CTA per SM, streams in several passes
@@ -946,72 +1083,146 @@ cudaError_t p25cu_launch_walk(const WalkParams& p, cudaStream_t st, unsigned max
 }
 
 // ---------------------------------------------------------------- event compaction
-// Per-stream slot counts -> exclusive offsets (one CTA; S <= a few hundred thousand).
-__global__ void __launch_bounds__(1024) p25_event_scan_kernel(const WalkState* states, unsigned n_streams, unsigned* offsets) {
-    __shared__ unsigned warp_tot[32];
-    __shared__ unsigned carry;
+// Per-stream event and word counts -> exclusive offsets (one CTA; S <= a few hundred thousand).  With a word capacity
+// (packed drain into a bounded host buffer) the totals cover only the leading streams that fit; the rest stay queued.
+__global__ void __launch_bounds__(1024) p25_event_scan_kernel(const WalkStateHbm* states, unsigned n_streams, unsigned* offsets,
+                                                              unsigned long long cap_words, unsigned* totals_out) {
+    __shared__ unsigned warp_tot[2][32];
+    __shared__ unsigned carry[2];
+    __shared__ unsigned fit_ev, fit_w, trunc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
+    if (threadIdx.x == 0) carry[0] = carry[1] = fit_ev = fit_w = trunc = 0;
     int ovf = 0;
     __syncthreads();
     for (unsigned base = 0; base < n_streams; base += 1024) {
         const unsigned s = base + threadIdx.x;
-        const unsigned v = s < n_streams ? states[s].n_events : 0;
-        if (s < n_streams) ovf |= (int)states[s].overflow;
-        unsigned x = v;
+        unsigned v[2] = {0, 0};
+        if (s < n_streams) {
+            v[0] = states[s].h.n_events;
+            v[1] = states[s].h.n_words;
+            ovf |= (int)states[s].h.overflow;
+        }
+        unsigned x[2] = {v[0], v[1]};
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned y = __shfl_up_sync(FULL, x, o);
-            if (lane >= o) x += y;
+            const unsigned y0 = __shfl_up_sync(FULL, x[0], o), y1 = __shfl_up_sync(FULL, x[1], o);
+            if (lane >= o) {
+                x[0] += y0;
+                x[1] += y1;
+            }
         }
-        if (lane == 31) warp_tot[warp] = x;
+        if (lane == 31) {
+            warp_tot[0][warp] = x[0];
+            warp_tot[1][warp] = x[1];
+        }
         __syncthreads();
-        if (warp == 0) {
-            unsigned t = warp_tot[lane];
+        if (warp < 2) {
+            unsigned t = warp_tot[warp][lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const unsigned y = __shfl_up_sync(FULL, t, o);
                 if (lane >= o) t += y;
             }
-            warp_tot[lane] = t;  // inclusive totals
+            warp_tot[warp][lane] = t;  // inclusive totals
         }
         __syncthreads();
-        const unsigned before = carry + (warp ? warp_tot[warp - 1] : 0) + (x - v);
-        if (s < n_streams) offsets[s] = before;
+        const unsigned before_ev = carry[0] + (warp ? warp_tot[0][warp - 1] : 0) + (x[0] - v[0]);
+        const unsigned before_w = carry[1] + (warp ? warp_tot[1][warp - 1] : 0) + (x[1] - v[1]);
+        if (s < n_streams) {
+            offsets[s] = before_ev;
+            offsets[n_streams + s] = before_w;
+            if ((unsigned long long)before_w + v[1] <= cap_words) {
+                if (v[0]) {
+                    atomicMax(&fit_ev, before_ev + v[0]);
+                    atomicMax(&fit_w, before_w + v[1]);
+                }
+            } else {
+                trunc = 1;
+            }
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = before + v;
+        if (threadIdx.x == 1023) {
+            carry[0] = before_ev + v[0];
+            carry[1] = before_w + v[1];
+        }
         __syncthreads();
     }
     ovf = __syncthreads_or(ovf);
     if (threadIdx.x == 0) {
-        offsets[n_streams] = carry;
-        offsets[n_streams + 1] = ovf ? 1u : 0u;
+        unsigned* t = offsets + 2 * (size_t)n_streams;
+        t[0] = trunc ? fit_ev : carry[0];
+        t[1] = trunc ? fit_w : carry[1];
+        t[2] = ovf ? 1u : 0u;
+        t[3] = trunc;
+        if (totals_out) {
+            totals_out[0] = t[0];
+            totals_out[1] = t[1];
+            totals_out[2] = t[2];
+            totals_out[3] = t[3];
+        }
     }
 }
 
-// One warp per stream copies its events to the dense array and clears the slot count.
-__global__ void __launch_bounds__(256) p25_event_gather_kernel(WalkState* states, const p25cu_event* slots, unsigned ev_cap,
+// One warp per stream expands its packed records into 80-byte p25cu_event records and clears the slot counters.
+__global__ void __launch_bounds__(256) p25_event_expand_kernel(WalkStateHbm* states, const unsigned* slots, unsigned ev_cap,
                                                                unsigned n_streams, const unsigned* offsets, p25cu_event* dense) {
     const unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (s >= n_streams) return;
-    const unsigned n = states[s].n_events;
-    const uint4* src = (const uint4*)(slots + (size_t)s * ev_cap);
-    uint4* dst = (uint4*)(dense + offsets[s]);
-    for (unsigned i = lane; i < n * 5; i += 32) dst[i] = src[i];
+    const unsigned n = states[s].h.n_events;
+    const unsigned* src = slots + (size_t)s * ev_cap * P25CU_SLOT_WORDS;
+    unsigned* dst = (unsigned*)(dense + offsets[s]);
+    unsigned cur = 0;
+    for (unsigned i = 0; i < n; i++) {
+        const unsigned w1 = src[cur + 1], w2 = src[cur + 2];      // uniform (broadcast) loads
+        const unsigned len = w2 >> 24, nw = p25cu_packed_words(len);
+        unsigned w = 0;
+        if (lane == 0) w = s;
+        else if (lane == 1) w = (w2 >> 16) & 0xFFu;               // kind
+        else if (lane == 2) w = w1;                               // sample, low half
+        else if (lane == 3) w = w2 & 0xFFFFu;                     // sample, bits 32..47
+        else if (lane == 4) w = len;
+        else if (lane < 20 && (unsigned)(lane - 5 + 3) < nw) w = src[cur + lane - 2];
+        if (lane < 20) dst[20 * i + lane] = w;
+        cur += nw;
+    }
     __syncwarp();
     if (lane == 0) {
-        states[s].n_events = 0;
-        states[s].overflow = 0;
+        states[s].h.n_events = 0;
+        states[s].h.n_words = 0;
+        states[s].h.overflow = 0;
     }
 }
 
-cudaError_t p25cu_launch_compact(const WalkState* states, const p25cu_event* slots, unsigned ev_cap, unsigned n_streams,
-                                 unsigned* offsets, p25cu_event* dense, cudaStream_t st) {
-    p25_event_scan_kernel<<<1, 1024, 0, st>>>(states, n_streams, offsets);
-    if (!dense) return cudaGetLastError();  // count only (p25cu_pending)
-    const unsigned blocks = (n_streams * 32 + 255) / 256;
-    p25_event_gather_kernel<<<blocks, 256, 0, st>>>(const_cast<WalkState*>(states), slots, ev_cap, n_streams, offsets, dense);
+// One warp per stream copies its packed words to the (stream, sample)-ordered output -- device memory or mapped
+// pinned host memory, in which case the stores themselves are the device-to-host transfer -- and clears the counters.
+// Streams beyond the output's capacity stay queued for the next drain.
+__global__ void __launch_bounds__(256) p25_event_pack_kernel(WalkStateHbm* states, const unsigned* slots, unsigned ev_cap,
+                                                             unsigned n_streams, const unsigned* offsets, unsigned* out,
+                                                             unsigned long long cap_words) {
+    const unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= n_streams) return;
+    const unsigned n = states[s].h.n_words, off = offsets[n_streams + s];
+    if ((unsigned long long)off + n > cap_words) return;
+    const unsigned* src = slots + (size_t)s * ev_cap * P25CU_SLOT_WORDS;
+    for (unsigned i = lane; i < n; i += 32) out[off + i] = src[i];
+    __syncwarp();
+    if (lane == 0) {
+        states[s].h.n_events = 0;
+        states[s].h.n_words = 0;
+        states[s].h.overflow = 0;
+    }
+}
+
+cudaError_t p25cu_launch_compact(WalkStateHbm* states, const unsigned* slots, unsigned ev_cap, unsigned n_streams,
+                                 unsigned* offsets, int mode, p25cu_event* dense80, unsigned* packed, unsigned long long cap_words,
+                                 unsigned* totals_out, cudaStream_t st) {
+    p25_event_scan_kernel<<<1, 1024, 0, st>>>(states, n_streams, offsets, mode == 2 ? cap_words : ~0ull, totals_out);
+    if (mode == 0) return cudaGetLastError();  // count only (p25cu_pending)
+    const unsigned blocks = (unsigned)(((size_t)n_streams * 32 + 255) / 256);
+    if (mode == 1) p25_event_expand_kernel<<<blocks, 256, 0, st>>>(states, slots, ev_cap, n_streams, offsets, dense80);
+    else p25_event_pack_kernel<<<blocks, 256, 0, st>>>(states, slots, ev_cap, n_streams, offsets, packed, cap_words);
     return cudaGetLastError();
 }
 
@@ -1041,6 +1252,10 @@ __global__ void p25_fec_selftest_kernel(const P25DevTables* tables, void* words,
         unsigned char out[12];
         out_nerr[i] = p25_trellis_half_decode(T, (const unsigned char*)words + i * 98, out);
         for (int j = 0; j < 12; j++) ((unsigned char*)out_data)[i * 12 + j] = out_nerr[i] < 0 ? 0 : out[j];
+    } else if constexpr (KIND == 14) {
+        unsigned char out[18];
+        out_nerr[i] = p25_trellis_34_decode(T, (const unsigned char*)words + i * 98, out);
+        for (int j = 0; j < 18; j++) ((unsigned char*)out_data)[i * 18 + j] = out_nerr[i] < 0 ? 0 : out[j];
     } else {
         unsigned pl[15];
         p25_imbe_decode(T, (const unsigned char*)words + i * 72, pl, pl + 8);
@@ -1049,8 +1264,8 @@ __global__ void p25_fec_selftest_kernel(const P25DevTables* tables, void* words,
     }
 }
 
-// The warp-cooperative decoders the walker uses, one warp per word: kinds 10 RS, 11 IMBE, 12 BCH, 13 half-rate trellis
-// (same inputs and outputs as kinds 7, 9, 0, 8).
+// The warp-cooperative decoders the walker uses, one warp per word: kinds 10 RS, 11 IMBE, 12 BCH, 13 half-rate trellis,
+// 15 3/4-rate trellis (same inputs and outputs as kinds 7, 9, 0, 8, 14).
 __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS) p25_fec_selftest_warp_kernel(const P25DevTables* tables, int kind, void* words,
                                                                                       size_t count, int n, int k, void* out_data,
                                                                                       int32_t* out_nerr) {
@@ -1086,6 +1301,14 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS) p25_fec_selftest_warp_k
             out_nerr[i] = r;
             ((unsigned*)out_data)[i] = d;
         }
+    } else if (kind == 15) {
+        for (int j = lane; j < 98; j += 32) buf[j] = ((const unsigned char*)words)[i * 98 + j];
+        __syncwarp();
+        unsigned char* out = scr + 128;
+        const int r = warp_trellis_34_decode(sh.T, sh.surv[warp], buf, lane, out);
+        __syncwarp();
+        if (lane < 18) ((unsigned char*)out_data)[i * 18 + lane] = r < 0 ? 0 : out[lane];
+        if (lane == 0) out_nerr[i] = r;
     } else {
         for (int j = lane; j < 98; j += 32) buf[j] = ((const unsigned char*)words)[i * 98 + j];
         __syncwarp();
@@ -1100,7 +1323,7 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS) p25_fec_selftest_warp_k
 cudaError_t p25cu_launch_fec_selftest(const P25DevTables* tables, int kind, void* words, size_t count, int n, int k,
                                       void* out_data, int32_t* out_nerr, cudaStream_t st) {
     if (count == 0) return cudaSuccess;
-    if (kind >= 10 && kind <= 13) {
+    if ((kind >= 10 && kind <= 13) || kind == 15) {
         const unsigned wb = (unsigned)((count + P25CU_WALK_WARPS - 1) / P25CU_WALK_WARPS);
         p25_fec_selftest_warp_kernel<<<wb, 32 * P25CU_WALK_WARPS, 0, st>>>(tables, kind, words, count, n, k, out_data, out_nerr);
         return cudaGetLastError();
@@ -1110,7 +1333,7 @@ cudaError_t p25cu_launch_fec_selftest(const P25DevTables* tables, int kind, void
 #define P25_ST_CASE(K) case K: p25_fec_selftest_kernel<K><<<blocks, 128, 0, st>>>(tables, words, count, n, k, out_data, out_nerr); break;
     switch (kind) {
         P25_ST_CASE(0) P25_ST_CASE(1) P25_ST_CASE(2) P25_ST_CASE(3) P25_ST_CASE(4)
-        P25_ST_CASE(5) P25_ST_CASE(6) P25_ST_CASE(7) P25_ST_CASE(8) P25_ST_CASE(9)
+        P25_ST_CASE(5) P25_ST_CASE(6) P25_ST_CASE(7) P25_ST_CASE(8) P25_ST_CASE(9) P25_ST_CASE(14)
         default: return cudaErrorInvalidValue;
     }
 #undef P25_ST_CASE

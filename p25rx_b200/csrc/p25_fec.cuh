@@ -41,6 +41,7 @@ struct alignas(16) P25DevTables {
     uint8_t ham15_cols[16];
     uint8_t ham10_cols[8];
     uint8_t trellis_pair[16];   // [prev state * 4 + next state] -> expected 4-bit dibit pair
+    uint8_t trellis34_pair[64]; // 3/4-rate: [prev state * 8 + next state] -> expected 4-bit dibit pair
     uint8_t interleave[52];
     uint8_t imbe_cw[144];
     uint8_t imbe_bit[144];
@@ -60,6 +61,7 @@ static inline void p25_fill_tables(P25DevTables* t) {
         t->ham15_cols[i] = i < 11 ? P25_HAMMING15_COLS[i] : 0;
         t->trellis_pair[i] = P25_CONSTELLATION[P25_TRELLIS_HALF[i]];
     }
+    for (int i = 0; i < 64; i++) t->trellis34_pair[i] = P25_CONSTELLATION[P25_TRELLIS_3_4[i]];
     for (int i = 0; i < 128; i++) t->gf_exp[i] = P25_GF_EXP[i];
     for (int i = 0; i < 64; i++) t->gf_log[i] = P25_GF_LOG[i];
     for (int i = 0; i < 8; i++) {
@@ -308,7 +310,7 @@ P25_FN int p25_rs_decode(const P25DevTables& T, uint8_t* sym, int n, int k) {
 }
 
 // ------------------------------------------------------------------ half-rate trellis (TSBK)
-#define P25_VITERBI_MAX_FIX 18  /* random blocks never get below ~22 (tests/test_oracle_fec.py) */
+
 // dibits: 98 received dibits (one per byte).  out12: decoded block.  Returns corrected bits or -1.
 // Add-compare-select over the 4 states; survivor decisions are kept as 2 bits per state per step.
 P25_FN int p25_trellis_half_decode(const P25DevTables& T, const uint8_t* dibits, uint8_t* out12) {
@@ -342,6 +344,62 @@ P25_FN int p25_trellis_half_decode(const P25DevTables& T, const uint8_t* dibits,
         st = (from[i] >> (2 * st)) & 3;
     }
     return m0;
+}
+
+// ------------------------------------------------------------------ 3/4-rate trellis (confirmed packet data blocks)
+// dibits: 98 received dibits.  out18: decoded block (48 tribits, MSB first).  Returns corrected bits or -1.
+// Eight path metrics in registers; the survivor of every state is kept as 3 bits of one word per step.
+P25_FN int p25_trellis_34_decode(const P25DevTables& T, const uint8_t* dibits, uint8_t* out18) {
+    int m[8];
+    m[0] = 0;
+#pragma unroll
+    for (int s = 1; s < 8; s++) m[s] = 1 << 20;
+    uint32_t from[49];
+    for (int i = 0; i < 49; i++) {
+        const int slot = T.interleave[i];
+        const int sym = (dibits[2 * slot] << 2) | dibits[2 * slot + 1];
+        int nm[8];
+        uint32_t packed = 0;
+#pragma unroll
+        for (int ns = 0; ns < 8; ns++) {
+            int key = ((m[0] + P25_POPC(T.trellis34_pair[ns] ^ sym)) << 3);
+#pragma unroll
+            for (int ps = 1; ps < 8; ps++) {
+                const int k2 = ((m[ps] + P25_POPC(T.trellis34_pair[8 * ps + ns] ^ sym)) << 3) | ps;
+                key = k2 < key ? k2 : key;      // equal metrics: the lower predecessor has the smaller key
+            }
+            nm[ns] = key >> 3;
+            packed |= (uint32_t)(key & 7) << (3 * ns);
+        }
+#pragma unroll
+        for (int s = 0; s < 8; s++) m[s] = nm[s];
+        from[i] = packed;
+    }
+    if (m[0] > P25_VITERBI34_MAX_FIX) return -1;
+    for (int i = 0; i < P25_PDU_BLOCK34_BYTES; i++) out18[i] = 0;
+    int st = 0;
+    for (int i = 48; i >= 0; i--) {
+        if (i < 48) {
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const int bit = 3 * i + b;
+                out18[bit >> 3] |= (uint8_t)(((st >> (2 - b)) & 1) << (7 - (bit & 7)));
+            }
+        }
+        st = (from[i] >> (3 * st)) & 7;
+    }
+    return m[0];
+}
+
+// CRC-CCITT of the P25 data blocks (TSBK, PDU header): x^16 + x^12 + x^5 + 1, zero start, inverted result
+P25_FN uint32_t p25_crc_ccitt(const uint8_t* data, int n) {
+    uint32_t crc = 0;
+    for (int i = 0; i < n; i++) {
+        crc ^= (uint32_t)data[i] << 8;
+        P25_ROLLED
+        for (int b = 0; b < 8; b++) crc = (crc & 0x8000) ? ((crc << 1) ^ 0x1021) & 0xFFFF : (crc << 1) & 0xFFFF;
+    }
+    return crc ^ 0xFFFF;
 }
 
 // ------------------------------------------------------------------ IMBE voice frame

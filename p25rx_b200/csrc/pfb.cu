@@ -310,19 +310,24 @@ cudaError_t p25cu_pfb_upload(float** d_taps, float2** d_twiddle) {
     return e;
 }
 
+// Per-device setup (once per device under the library's plan mutex, that device current).
+cudaError_t p25cu_pfb_plan_device(P25DevPlan* plan) {
+    cudaError_t e = cudaFuncSetAttribute(pfb::p25_pfb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pfb::SmemA));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(pfb::p25_chan_fm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pfb::SmemB));
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pfb::p25_pfb_kernel, pfb::NT, sizeof(pfb::SmemA));
+    if (e != cudaSuccess) return e;
+    plan->pfb_slots = plan->n_sm * (per_sm > 0 ? per_sm : 1);
+    return cudaSuccess;
+}
+
 // One chunk of every capture: spectrum rows into y (rows hist ..), baseband rows into bb, new tail.
 cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out, const float* taps, const float2* twiddle, float2* y,
                              unsigned y_rows, float* bb, size_t row_stride, float* power_sum, unsigned long long a0,
                              unsigned long long m0, unsigned n, unsigned n_out, unsigned n_captures, cudaStream_t st,
-                             unsigned* launches) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(pfb::p25_pfb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pfb::SmemA));
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(pfb::p25_chan_fm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pfb::SmemB));
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+                             unsigned* launches, const P25DevPlan* plan) {
     const unsigned hist = p25cu_pfb_hist_rows();
     if (n_out) {
         pfb::PfbParams a;
@@ -340,14 +345,7 @@ cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out
         a.hist = hist;
         // one wave of CTAs: consecutive output times per CTA (their windows overlap, so re-reads hit L1), as many CTAs
         // as fit at once
-        static int slots = 0;
-        if (!slots) {
-            int dev = 0, n_sm = 0, per_sm = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pfb::p25_pfb_kernel, pfb::NT, sizeof(pfb::SmemA));
-            slots = n_sm * (per_sm > 0 ? per_sm : 1);
-        }
+        const int slots = plan->pfb_slots;
         unsigned per_cap = (unsigned)slots / n_captures;
         if (per_cap < 1) per_cap = 1;
         const unsigned tpc = (n_out + per_cap - 1) / per_cap;            // output times per CTA

@@ -116,6 +116,54 @@ class Context:
         self._ck(self._L.p25cu_poll(self._h, ev.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
         return ev[: n.value]
 
+    # ---- packed, asynchronous drain (p25cu_poll_start / p25cu_poll_packed)
+    def poll_start(self):
+        """Queue the compaction of everything decoded so far; returns at once (at most two outstanding)."""
+        self._ck(self._L.p25cu_poll_start(self._h))
+
+    def poll_packed(self, copy: bool = True):
+        """Collect the oldest started poll (starting one if none is outstanding): (u32 words, n_events, more).
+        copy=False returns a view of the context's pinned buffer, valid until two further polls have been started."""
+        ptr, nw, ne, more = C.c_void_p(), C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+        self._ck(self._L.p25cu_poll_packed(self._h, C.byref(ptr), C.byref(nw), C.byref(ne), C.byref(more)))
+        if nw.value == 0:
+            return np.zeros(0, dtype=np.uint32), 0, bool(more.value)
+        buf = (C.c_uint32 * nw.value).from_address(ptr.value)
+        words = np.frombuffer(buf, dtype=np.uint32, count=nw.value)
+        return (words.copy() if copy else words), ne.value, bool(more.value)
+
+    def unpack(self, words: np.ndarray, n_events: int) -> np.ndarray:
+        """Packed records -> the 80-byte event records poll() returns (host-side byte shuffling)."""
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        ev = np.zeros(max(n_events, 1), dtype=EVENT_DTYPE)
+        n = C.c_size_t(0)
+        self._ck(self._L.p25cu_unpack_events(words.ctypes.data_as(C.c_void_p), words.size, ev.ctypes.data_as(C.c_void_p), n_events,
+                                             C.byref(n)))
+        return ev[: n.value]
+
+    # ---- pinned host buffers (the reference's buffer pools, src/demod.rs:63, src/sdr.rs:25-33)
+    def host_alloc(self, shape, dtype) -> np.ndarray:
+        """A page-locked numpy array owned by the library; release with host_free(arr)."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._ck(self._L.p25cu_host_alloc(self._h, nbytes, C.byref(p)))
+        buf = (C.c_char * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p.value
+        return arr
+
+    def host_free(self, arr: np.ndarray):
+        p = self._pinned.pop(arr.ctypes.data)
+        self._ck(self._L.p25cu_host_free(self._h, C.c_void_p(p)))
+
+    def host_register(self, arr: np.ndarray):
+        self._ck(self._L.p25cu_host_register(self._h, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
+    def host_unregister(self, arr: np.ndarray):
+        self._ck(self._L.p25cu_host_unregister(self._h, arr.ctypes.data_as(C.c_void_p)))
+
     def resync(self, stream: int):
         self._ck(self._L.p25cu_resync(self._h, stream))
 
@@ -123,6 +171,12 @@ class Context:
         st = _lib.Stats()
         self._ck(self._L.p25cu_get_stats(self._h, stream, C.byref(st), int(clear)))
         return np.ctypeslib.as_array(st.code).astype(np.uint64).reshape(12, 4).copy()
+
+    def read_baseband(self, stream: int, n: int) -> np.ndarray:
+        """First n baseband samples of one stream of the last demod / process (device -> host)."""
+        out = np.empty(n, dtype=np.float32)
+        self._ck(self._L.p25cu_read_baseband(self._h, stream, out.ctypes.data_as(C.c_void_p), n))
+        return out
 
     def channelizer_output(self) -> np.ndarray:
         """Channelizer mode (decimation 400): channel spectra of the last demod, [captures][n_out][1536] complex64."""
@@ -155,7 +209,7 @@ class Context:
 
     def fec_selftest(self, kind: int, words: np.ndarray, n: int = 0, k: int = 0):
         words = np.ascontiguousarray(words)
-        warp_kind, kind = kind, {10: 7, 11: 9, 12: 0, 13: 8}.get(kind, kind)   # 10..13: warp-cooperative forms
+        warp_kind, kind = kind, {10: 7, 11: 9, 12: 0, 13: 8, 15: 14}.get(kind, kind)   # 10..13, 15: warp-cooperative forms
         if kind == 0:
             count, out = words.size, np.zeros(words.size, dtype=np.uint32)
         elif kind == 7:
@@ -166,6 +220,9 @@ class Context:
         elif kind == 9:
             count = words.size // 72
             out = np.zeros((count, 15), dtype=np.uint32)
+        elif kind == 14:
+            count = words.size // 98
+            out = np.zeros((count, 18), dtype=np.uint8)
         else:
             count, out = words.size, np.zeros(words.size, dtype=np.uint32)
         nerr = np.zeros(count, dtype=np.int32)

@@ -447,7 +447,20 @@ def tsbk_block_dibits(payload12: bytes) -> np.ndarray:
     assert len(payload12) == 12
     bits = np.unpackbits(np.frombuffer(bytes(payload12), dtype=np.uint8))
     dibits = [(int(bits[2 * i]) << 1) | int(bits[2 * i + 1]) for i in range(48)]
-    pts = trellis_half_encode(dibits)
+    return _points_to_dibits(trellis_half_encode(dibits))
+
+
+def trellis_34_encode(tribits48: list[int]) -> list[int]:
+    """48 tribits + flush -> 49 constellation points (3/4-rate, 8 states; next state = input tribit) [STD]."""
+    state = 0
+    out = []
+    for t in list(tribits48) + [0]:
+        out.append(TRELLIS_3_4[state][t])
+        state = t
+    return out
+
+
+def _points_to_dibits(pts: list[int]) -> np.ndarray:
     perm = interleave_perm()
     slots = [0] * 49
     for i, p in enumerate(pts):
@@ -457,6 +470,57 @@ def tsbk_block_dibits(payload12: bytes) -> np.ndarray:
         out[2 * s] = (v >> 2) & 3
         out[2 * s + 1] = v & 3
     return out
+
+
+PDU_BLOCK34_BYTES = 18
+
+
+def pdu_block34_dibits(payload18: bytes) -> np.ndarray:
+    """18-byte confirmed-data block -> 98 transmitted dibits (3/4-rate trellis + the data interleaver) [STD]."""
+    assert len(payload18) == PDU_BLOCK34_BYTES
+    bits = np.unpackbits(np.frombuffer(bytes(payload18), dtype=np.uint8))
+    tribits = [(int(bits[3 * i]) << 2) | (int(bits[3 * i + 1]) << 1) | int(bits[3 * i + 2]) for i in range(48)]
+    return _points_to_dibits(trellis_34_encode(tribits))
+
+
+# Packet data unit header [STD layout, RECALL]: octet 0 = 0 | A/N | I/O | format(5); octet 1 = 1 1 | SAP(6); octet 2 MFID;
+# octets 3-5 logical link id; octet 6 = FMF | blocks to follow (7); octet 7 pad count; octet 8 Syn | N(S) | FSNF;
+# octet 9 data header offset; octets 10-11 CRC-CCITT of octets 0-9.  Format 0x16 = confirmed data (3/4-rate blocks of
+# 18 octets), 0x15 = unconfirmed data (1/2-rate blocks of 12 octets).
+PDU_FORMAT_CONFIRMED = 0x16
+PDU_FORMAT_UNCONFIRMED = 0x15
+PDU_MAX_BLOCKS = 127
+
+
+def pdu_header(fmt: int, blocks_to_follow: int, sap: int = 0x04, mfid: int = 0, llid: int = 0x123456, pad: int = 0,
+               bad_crc: bool = False) -> bytes:
+    head = bytes([0x40 | (fmt & 0x1F), 0xC0 | (sap & 0x3F), mfid & 0xFF, (llid >> 16) & 0xFF, (llid >> 8) & 0xFF, llid & 0xFF,
+                  0x80 | (blocks_to_follow & 0x7F), pad & 0x1F, 0x00, 0x00])
+    crc = crc_ccitt_p25(head)
+    if bad_crc:
+        crc ^= 0x0440
+    return head + bytes([crc >> 8, crc & 0xFF])
+
+
+def crc9_p25(bits) -> int:
+    """CRC-9 of a confirmed data block [RECALL: g = x^9+x^6+x^4+x^3+1, inverted]; carried, never checked by the
+    MessageReceiver surface (no event holds packet data)."""
+    crc = 0
+    for b in bits:
+        crc = ((crc << 1) | int(b)) & 0x3FF
+        if crc & 0x200:
+            crc ^= 0x259
+    for _ in range(9):
+        crc = (crc << 1) & 0x3FF
+        if crc & 0x200:
+            crc ^= 0x259
+    return (crc ^ 0x1FF) & 0x1FF
+
+
+# Path-metric bounds above which a trellis block is reported undecodable [BUILD]: random 98-dibit blocks decode to
+# metric >= 22 (1/2 rate) and >= 8 (3/4 rate) (tests/test_oracle_fec.py).
+VITERBI_MAX_FIX = 18
+VITERBI34_MAX_FIX = 6
 
 
 def crc_ccitt_p25(data: bytes) -> int:

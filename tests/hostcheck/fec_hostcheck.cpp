@@ -25,5 +25,7 @@ int hc_hamming10_decode(uint32_t w, uint32_t* d) { return p25_hamming10_decode(T
 int hc_cyclic16_decode(uint32_t w, uint32_t* d) { return p25_cyclic16_decode(T(), w, d); }
 int hc_rs_decode(uint8_t* sym, int n, int k) { return p25_rs_decode(T(), sym, n, k); }
 int hc_trellis_half_decode(const uint8_t* d98, uint8_t* out12) { return p25_trellis_half_decode(T(), d98, out12); }
+int hc_trellis_34_decode(const uint8_t* d98, uint8_t* out18) { return p25_trellis_34_decode(T(), d98, out18); }
+uint32_t hc_crc_ccitt(const uint8_t* d, int n) { return p25_crc_ccitt(d, n); }
 void hc_imbe_decode(const uint8_t* d72, uint32_t* c, uint32_t* e) { p25_imbe_decode(T(), d72, c, e); }
 }

@@ -80,8 +80,9 @@ def test_error_paths(oracle):
     ev = oracle.MessageReceiver().feed(bb)
     assert int(ev[1]["kind"]) == tx.EV_TSBK
     # 4. packet data units and simple terminators produce a NID only
-    for duid in (0xC, 0x3):
-        un = tx._assemble(0x293, duid, np.zeros(0, np.uint8), [])
+    rng = np.random.default_rng(4)
+    pdu = tx.pdu(0x293, True, [tx.confirmed_block(j, rng.integers(0, 256, 16).astype(np.uint8).tobytes()) for j in range(3)])
+    for duid, un in ((0xC, pdu), (0x3, tx._assemble(0x293, 0x3, np.zeros(0, np.uint8), []))):
         bb, _ = tx.baseband_48k(tx.concat_units([un, tx.tsdu(0x293, [tx.make_tsbk(1, 0, bytes(8), True)])], lead_idle=30, gap_idle=300).dibits)
         ev = oracle.MessageReceiver().feed(bb)
         assert [int(k) for k in ev["kind"]] == [tx.EV_NID, tx.EV_NID, tx.EV_TSBK]
@@ -114,3 +115,30 @@ def test_noise_only_produces_no_lock(oracle):
     ev = oracle.MessageReceiver().feed(bb)
     assert len(ev) <= 2      # false locks on noise are possible but rare; they can only yield errors
     assert all(int(k) == tx.EV_ERROR for k in ev["kind"])
+
+
+def test_packet_data_units(oracle):
+    """SURVEY 8a a9.9: a PDU yields its PacketNID only (no MessageEvent variant carries packet data, src/recv.rs:214-233);
+    header and unconfirmed blocks count as viterbiDibit words, confirmed blocks as viterbiTribit words (src/hub.rs:569-570);
+    a destroyed confirmed block is a ViterbiTribit error; a header whose CRC fails drops the lock silently."""
+    st = tx.data_channel(21, 6)
+    bb, _ = tx.baseband_48k(st.dibits, snr_db=20, seed=1)
+    rx = oracle.MessageReceiver()
+    ev = rx.feed(bb)
+    check_against_truth(ev, tx.expected_events(st))
+    stats = rx.stats()
+    n_conf = sum(1 for i in range(0, 6, 2))          # PDUs 0, 2, 4 are confirmed
+    assert stats[11, 0] > 0 and stats[11, 1] == 0 and stats[10, 0] > 6      # tribit words seen, none failed
+    # destroy one confirmed data block: Error(ViterbiTribit), then resync and the following TSDU decodes
+    rng = np.random.default_rng(2)
+    pdu = tx.pdu(0x293, True, [tx.confirmed_block(j, bytes(16)) for j in range(2)])
+    d = tx.concat_units([pdu, tx.tsdu(0x293, [tx.make_tsbk(3, 0, bytes(8), True)])], lead_idle=30, gap_idle=40).dibits.copy()
+    blk = 30 + 24 + 32 + 98 + 98 + 6             # inside the second data block (status symbols shift it a little)
+    d[blk + 10: blk + 80] = rng.integers(0, 4, 70)
+    ev = oracle.MessageReceiver().feed(tx.baseband_48k(d)[0])
+    assert [int(k) for k in ev["kind"]] == [tx.EV_NID, tx.EV_ERROR, tx.EV_NID, tx.EV_TSBK] and int(ev[1]["payload"][0]) == 4
+    # header CRC failure: no event besides the NID, lock dropped, next unit decodes
+    bad = tx.pdu(0x293, True, [tx.confirmed_block(0, bytes(16))], bad_header_crc=True)
+    d = tx.concat_units([bad, tx.tsdu(0x293, [tx.make_tsbk(3, 0, bytes(8), True)])], lead_idle=30, gap_idle=200).dibits
+    ev = oracle.MessageReceiver().feed(tx.baseband_48k(d)[0])
+    assert [int(k) for k in ev["kind"]] == [tx.EV_NID, tx.EV_NID, tx.EV_TSBK]

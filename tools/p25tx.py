@@ -111,6 +111,42 @@ def tdulc(nac: int, lc: bytes) -> Unit:
     return _assemble(nac, S.DUID_TDULC, _bits_to_dibits(bits), [(EV_VOICE_TERM, bytes(lc), S.TDULC_DIBITS)])
 
 
+def pdu(nac: int, confirmed: bool, blocks: list[bytes], bad_header_crc: bool = False, announce: int | None = None) -> Unit:
+    """Packet data unit [STD]: 1/2-rate header block, then `blocks` -- 18-byte confirmed-data blocks (3/4-rate) or
+    12-byte unconfirmed ones (1/2-rate).  The receiver surface has no event for packet data (src/recv.rs:214-233): the
+    only expected event is the PacketNID.  announce overrides the header's blocks-to-follow field."""
+    n_follow = len(blocks) if announce is None else announce
+    head = S.pdu_header(S.PDU_FORMAT_CONFIRMED if confirmed else S.PDU_FORMAT_UNCONFIRMED, n_follow, bad_crc=bad_header_crc)
+    parts = [S.tsbk_block_dibits(head)]
+    for b in blocks:
+        parts.append(S.pdu_block34_dibits(b) if confirmed else S.tsbk_block_dibits(b))
+    return _assemble(nac, S.DUID_PDU, np.concatenate(parts), [])
+
+
+def confirmed_block(serial: int, data16: bytes) -> bytes:
+    """18-byte confirmed data block: 7-bit serial number, CRC-9 over serial + data, 16 data octets [STD layout, RECALL]."""
+    assert len(data16) == 16
+    bits = _bits_msb(serial & 0x7F, 7) + list(np.unpackbits(np.frombuffer(bytes(data16), dtype=np.uint8)))
+    crc = S.crc9_p25(bits)
+    return bytes([((serial & 0x7F) << 1) | (crc >> 8), crc & 0xFF]) + bytes(data16)
+
+
+def data_channel(seed: int, n_pdu: int, nac: int = 0x293, lead_idle: int = 40) -> Stream:
+    """Packet data traffic: confirmed and unconfirmed PDUs of 1..4 blocks between TSDUs (exercises the 3/4-rate trellis,
+    SURVEY.md 8a a9.9)."""
+    rng = np.random.default_rng(seed)
+    units = []
+    for i in range(n_pdu):
+        nb = int(rng.integers(1, 5))
+        if i % 2 == 0:
+            blocks = [confirmed_block(j, rng.integers(0, 256, 16).astype(np.uint8).tobytes()) for j in range(nb)]
+            units.append(pdu(nac, True, blocks))
+        else:
+            units.append(pdu(nac, False, [rng.integers(0, 256, 12).astype(np.uint8).tobytes() for _ in range(nb)]))
+        units.append(tsdu(nac, [make_tsbk(int(rng.integers(0, 64)), 0, rng.integers(0, 256, 8).astype(np.uint8).tobytes(), last=True)]))
+    return concat_units(units, lead_idle=lead_idle, gap_idle=6, rng=rng)
+
+
 def _vf_payload(u: list[int]) -> bytes:
     return np.array(list(u) + [0] * 7, dtype="<u4").tobytes()
 
