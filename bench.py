@@ -430,15 +430,21 @@ def measure(wl: Workload, rank: int, local: int, K: int, W: int, barrier, gate_o
             gpu_ev.append(e[np.isin(e["stream"], orc.streams)].copy())
         return ne
 
-    def drain():
-        """Collect every queued event (several polls if the pinned buffer cannot hold them at once): (events, bytes)."""
-        tot, nbytes = 0, 0
+    def drain_raw():
+        """Collect every queued event (several polls if the pinned buffer cannot hold them at once).  No host-side
+        processing here: the views stay valid until two further polls are started, so only a multi-poll drain copies."""
+        got = []
         while True:
             w, ne, more = ctx.poll_packed(copy=False)
-            tot += take(w, ne)
-            nbytes += 4 * len(w) + 16
+            got.append((w.copy() if more or got else w, ne))
             if not more:
-                return tot, nbytes
+                return got
+
+    def account(got):
+        return sum(take(w, ne) for w, ne in got), sum(4 * len(w) + 16 for w, _ in got)
+
+    def drain():
+        return account(drain_raw())
 
     # ---------------- leg 1: device-resident input ("value") + the demod kernel's own event-timed duration
     n_events = 0
@@ -460,8 +466,11 @@ def measure(wl: Workload, rank: int, local: int, K: int, W: int, barrier, gate_o
             ctx.process(dev, n)                          # demod kernel, then the decode walker (beside the next demod kernel)
         gate.open()
         out["enqueue_ms"] = 1e3 * (time.perf_counter() - t_host0)
-        burst_events, out["d2h_burst_bytes"] = drain()   # packed compaction straight into pinned host memory (synchronises)
+        raw = drain_raw()                                # packed compaction straight into pinned host memory (synchronises)
         t_end.record(stream)
+    burst_events, out["d2h_burst_bytes"] = account(raw)
+    with torch.cuda.stream(stream):
+        pass
     barrier()
     out["launches"] = ctx.launch_count - l0
     out["dev_ms"] = t_begin.elapsed_time(t_end)

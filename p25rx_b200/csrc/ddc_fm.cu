@@ -354,7 +354,10 @@ struct F {
 #ifndef DDC50_MAXREG
 #define DDC50_MAXREG 56
 #endif
-    static constexpr int MAXREG = U8 ? 64 : DDC50_MAXREG;
+#ifndef DDC50_U8_MAXREG
+#define DDC50_U8_MAXREG 48
+#endif
+    static constexpr int MAXREG = U8 ? DDC50_U8_MAXREG : DDC50_MAXREG;
 };
 
 template <int FMT>

@@ -195,7 +195,7 @@ def test_pinned_host_buffers_and_sequence_rules(p25, oracle):
     returns (double-buffered staging on a copy stream); results equal the oracle's.  demod, demod, decode(NULL) once
     decoding has begun is a call-sequence error instead of a silently skipped chunk."""
     S_, chunk, n_chunks = 6, 16384, 5
-    rows = [tx.iq_to_u8(tx.modulate_iq(tx.control_channel(7000 + s, 4).dibits, 240_000, snr_db=20, cfo_hz=30.0 * s, seed=s))
+    rows = [tx.iq_to_u8(tx.modulate_iq(tx.control_channel(7000 + s, 6).dibits, 240_000, snr_db=20, cfo_hz=30.0 * s, seed=s))
             for s in range(S_)]
     assert min(len(r) for r in rows) >= 2 * chunk * n_chunks
     data = np.stack([r[: 2 * chunk * n_chunks] for r in rows])
@@ -281,7 +281,7 @@ def test_cfg2_bench_geometry_sampled_against_oracle(p25, oracle):
     ctx = p25.Context(S_, fmt=p25.FMT_CF32_IQ, decimation=50, max_chunk_samples=n, event_slots=64)
     bps, grid = 113, 148 * 3                                                  # blocks per stream, CTAs (3 per SM)
     n_static = (S_ * bps // grid) * 7 // 8
-    straddlers = sorted({(n_static * b) // bps for b in range(1, grid, 11)})  # streams a static share begins inside
+    straddlers = sorted({(n_static * b) // bps for b in range(1, grid, 8)})   # streams a static share begins inside
     sample = sorted(set([0, 1, 2, S_ - 2, S_ - 1] + straddlers + list(range((n_static * grid) // bps, S_, 9))))
     assert len(sample) >= 64
     worst, n_ev = _sampled_compare(p25, oracle, ctx, dev, base, n, False, 50, sample, 3)
