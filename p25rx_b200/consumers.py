@@ -178,18 +178,105 @@ class LinkControlFields:
         return self.raw[1:9]
 
 
-def collect_talkgroups(events: np.ndarray, channels: ChannelParamsMap):
+def _be(p: bytes) -> int:
+    return int.from_bytes(p, "big")
+
+
+def hub_status_event(kind: int, raw: bytes, channels: "ChannelParamsMap"):
+    """The JSON objects the hub streams for one TrunkingControl (kind 7) or LinkControl / VoiceTerm (3 / 8) event
+    (src/hub.rs:346-404, :405-443, :525-547): a list of (event name, payload).  Same [STD]-from-memory layouts as
+    include/p25cu.hpp `fields::`."""
+    out = []
+
+    def freq(ch: Channel):
+        p = channels.lookup(ch.id)
+        return None if p is None else p.rx_freq(ch.number)
+
+    def rfss(p):
+        out.append(("rfssStatus", {"area": p[0], "system": (p[1] & 0xF) << 8 | p[2], "rfss": p[3], "site": p[4]}))
+
+    def net(p):
+        out.append(("networkStatus", {"area": p[0], "wacn": p[1] << 12 | p[2] << 4 | p[3] >> 4, "system": (p[3] & 0xF) << 8 | p[4]}))
+
+    def adjacent(p):
+        f = freq(Channel.from_bits(_be(p[5:7])))
+        if f is not None:
+            out.append(("adjacentSite", {"area": p[0], "rfss": p[3], "system": (p[1] & 0xF) << 8 | p[2], "site": p[4], "freq": f}))
+
+    def alt(p):
+        for ch in (Channel.from_bits(_be(p[2:4])), Channel.from_bits(_be(p[5:7]))):
+            f = freq(ch)
+            if f is not None:
+                out.append(("altControl", {"rfss": p[0], "site": p[1], "freq": f}))
+
+    if kind == 7:
+        t = TsbkFields(raw[:12])
+        if t.mfg() != 0 or not t.crc_valid() or t.opcode() is None:
+            return out
+        p, op = t.payload(), t.opcode()
+        if op == "RfssStatusBroadcast":
+            rfss(p)
+        elif op == "NetworkStatusBroadcast":
+            net(p)
+        elif op == "AltControlChannel":
+            alt(p)
+        elif op == "AdjacentSite":
+            adjacent(p)
+        elif op == "LocRegResponse":
+            out.append(("locReg", {"response": p[0] & 3, "rfss": p[3], "site": p[4], "unit": _be(p[5:8])}))
+        elif op == "UnitRegResponse":
+            out.append(("unitReg", {"response": (p[0] >> 4) & 3, "system": (p[0] & 0xF) << 8 | p[1], "unitId": _be(p[2:5]), "unitAddr": _be(p[5:8])}))
+        elif op == "UnitDeregAck":
+            out.append(("unitDereg", {"wacn": p[1] << 12 | p[2] << 4 | p[3] >> 4, "system": (p[3] & 0xF) << 8 | p[4], "unit": _be(p[5:8])}))
+    elif kind in (3, 8):
+        lc = LinkControlFields(raw[:9])
+        op, p = lc.opcode(), lc.payload()
+        if op == "GroupVoiceTraffic":
+            out.append(("srcUnit", _be(raw[6:9])))
+        elif op == "RfssStatusBroadcast":
+            rfss(p)
+        elif op == "NetworkStatusBroadcast":
+            net(p)
+        elif op == "AdjacentSite":
+            adjacent(p)
+        elif op == "AltControlChannel":
+            alt(p)
+    return out
+
+
+def talkgroup_other(tg: int) -> bool:
+    """TalkGroup::Other(_) (src/recv.rs:327-330): not Nobody (0x0000), Default (0x0001) or Everybody (0xFFFF)."""
+    return tg not in (0x0000, 0x0001, 0xFFFF)
+
+
+def consume(events: np.ndarray):
+    """One RecvTask + hub per stream over a drained event array: returns (talkgroups [(stream, sample, tg, rx_freq)],
+    hub [(stream, json text)]) in the order tests/cpp/p25host_main prints them in its `consumer` mode."""
+    tgs, hub = [], []
+    for s in sorted(set(int(x) for x in events["stream"])):
+        ch = ChannelParamsMap()
+        ev = events[events["stream"] == s]
+        tgs += collect_talkgroups(ev, ch, hub_out=hub)
+    return tgs, hub
+
+
+def collect_talkgroups(events: np.ndarray, channels: ChannelParamsMap, hub_out: list | None = None):
     """What RecvTask::handle_tsbk / handle_lc / add_talkgroup make of a drained event array (src/recv.rs:237-342):
     returns [(stream, sample, talkgroup, rx_freq_hz)] for every grant / update whose channel identifier is known."""
     out = []
 
     def add(ev, tg, ch):
         p = channels.lookup(ch.id)
-        if p is not None and tg != 0:
+        if p is not None and talkgroup_other(tg):
             out.append((int(ev["stream"]), int(ev["sample"]), tg, p.rx_freq(ch.number)))
 
     for ev in events:
         kind = int(ev["kind"])
+        if hub_out is not None and kind in (3, 7, 8):
+            pending_hub = [(int(ev["stream"]), json.dumps({"event": n, "payload": pl})) for n, pl in
+                           hub_status_event(kind, bytes(ev["payload"][:12]), channels)]
+        else:
+            pending_hub = []
         if kind == 7:
             t = TsbkFields(bytes(ev["payload"][:12]))
             if t.mfg() != 0 or not t.crc_valid():
@@ -203,11 +290,13 @@ def collect_talkgroups(events: np.ndarray, channels: ChannelParamsMap):
             elif op == "GroupVoiceUpdate":
                 for ch, tg in group_traffic_updates(t.payload()):
                     add(ev, tg, ch)
-        elif kind == 3:
+        elif kind in (3, 8):      # LinkControl and VoiceTerm(lc) both go through handle_lc (src/recv.rs:229, :232)
             lc = LinkControlFields(bytes(ev["payload"][:9]))
             if lc.opcode() == "GroupVoiceUpdate":
                 for ch, tg in group_traffic_updates(lc.payload()):
                     add(ev, tg, ch)
+        if hub_out is not None:
+            hub_out += pending_hub
     return out
 
 

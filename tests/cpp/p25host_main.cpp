@@ -4,7 +4,13 @@
 //   p25host_main replay a.f32 b.f32 ...   src/replay.rs:26-57: f32le 48 kHz recordings -> ReplayReceiver
 //   p25host_main sdr a.u8 b.u8 ...        src/sdr.rs:25-33 + src/demod.rs:62-119 + src/recv.rs:140-167:
 //                                         32,768-byte u8 IQ chunks -> DemodTask -> MessageReceiver
+//   p25host_main consumer a.f32 ...       replay, then every stream's events through p25cu::RecvConsumer: what RecvTask
+//                                         and the hub make of them (src/recv.rs:237-342, src/hub.rs:335-443)
+//   p25host_main fields KIND:HEX ...      no GPU: one event per argument (KIND = 7 TSBK, 3 LinkControl, 8 VoiceTerm;
+//                                         HEX = payload) through RecvConsumer
 // Lines:  E <stream> <sample> <kind> <len> <payload hex>     one per MessageEvent, in delivery order
+//         T <stream> <sample> <talkgroup> <rx_freq_hz>       add_talkgroup (src/recv.rs:325-342)
+//         H <stream> <json>                                  one hub SerdeEvent (src/hub.rs:505-523)
 //         P <chunk> <stream> <dBm>                           signal power (every 4th chunk)
 //         B <chunk> <n_out>                                  baseband samples per stream produced by the chunk
 //         S <family> <words> <errs> <fixed>                  merged stats;   V <n> voice frames handed to the audio sink
@@ -34,6 +40,23 @@ int main(int argc, char** argv) {
         return 2;
     }
     const std::string mode = argv[1];
+    if (mode == "fields") {
+        p25cu::RecvConsumer rc;
+        for (int i = 2; i < argc; i++) {
+            const std::string a = argv[i];
+            p25cu::MessageEvent e{};
+            e.stream = 0;
+            e.sample = (unsigned long long)(i - 2);
+            e.kind = static_cast<p25cu::MessageEvent::Kind>(std::stoi(a.substr(0, a.find(':'))));
+            const std::string hex = a.substr(a.find(':') + 1);
+            e.len = (uint32_t)(hex.size() / 2);
+            for (uint32_t b = 0; b < e.len && b < 60; b++) e.payload[b] = (uint8_t)std::stoi(hex.substr(2 * b, 2), nullptr, 16);
+            rc.handle(e);
+        }
+        for (const auto& t : rc.talkgroups) std::printf("T 0 %llu %u %llu\n", (unsigned long long)t.sample, t.tg, (unsigned long long)t.rx_freq);
+        for (const auto& j : rc.hub_json) std::printf("H 0 %s\n", j.c_str());
+        return 0;
+    }
     std::vector<std::unique_ptr<std::ifstream>> files;
     for (int i = 2; i < argc; i++) {
         files.emplace_back(new std::ifstream(argv[i], std::ios::binary));
@@ -44,7 +67,18 @@ int main(int argc, char** argv) {
     }
     const uint32_t S = (uint32_t)files.size();
     try {
-        if (mode == "replay") {
+        if (mode == "consumer") {
+            p25cu::ReplayReceiver rx(S, nullptr);
+            std::vector<std::istream*> in;
+            for (auto& f : files) in.push_back(f.get());
+            rx.replay(in);
+            std::vector<p25cu::RecvConsumer> rc(S);          // one RecvTask per stream, like one p25rx process per channel
+            for (const auto& e : rx.events()) rc[e.stream].handle(e);
+            for (uint32_t s = 0; s < S; s++) {
+                for (const auto& t : rc[s].talkgroups) std::printf("T %u %llu %u %llu\n", s, (unsigned long long)t.sample, t.tg, (unsigned long long)t.rx_freq);
+                for (const auto& j : rc[s].hub_json) std::printf("H %u %s\n", s, j.c_str());
+            }
+        } else if (mode == "replay") {
             unsigned long long voice = 0;
             p25cu::ReplayReceiver rx(S, [&](const p25cu::MessageEvent& e) {
                 const p25cu::VoiceFrame vf = e.voice_frame();     // what AudioTask::play receives (src/audio.rs:75-87)

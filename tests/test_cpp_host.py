@@ -108,3 +108,122 @@ def test_cpp_demod_task_and_receiver_match_oracle(tmp_path):
     for c, s, v in pw:
         assert abs(v - ref_pw[(c, s)]) < 1e-2
     assert st["viterbiDibit"][0] == sum(1 for e in ev if e[2] == 7)
+
+
+# ------------------------------------------------------------------ SURVEY 8f rank 2 in the compiled host layer
+def _chan_params(ident, base_hz=851_012_500, spacing_hz=12_500, bw_hz=12_500, offset=(1, 45)):
+    v = (ident << 60) | ((bw_hz // 125) << 51) | (((0x100 if offset[0] > 0 else 0) | offset[1]) << 42) | ((spacing_hz // 125) << 32) | (base_hz // 5)
+    return v.to_bytes(8, "big")
+
+
+def _consumer_units():
+    """TSBKs and link-control words whose fields the reference's consumers read (src/recv.rs:237-342, src/hub.rs:346-443)."""
+    ch = lambda ident, number: ((ident << 12) | number).to_bytes(2, "big")
+    sysid, wacn = 0x2A5, 0xBEE07
+    status = bytes([0x11, 0x10 | (sysid >> 8), sysid & 0xFF, 0x07, 0x21]) + ch(1, 0x155) + bytes([0x70])
+    tsbks = [
+        (0x3D, _chan_params(1)),                                                            # ChannelParamsUpdate
+        (0x00, bytes([0x04]) + ch(1, 0x123) + (0x4567).to_bytes(2, "big") + (0xABCDEF).to_bytes(3, "big")),   # GroupVoiceGrant
+        (0x02, ch(1, 0x010) + (100).to_bytes(2, "big") + ch(2, 0x020) + (200).to_bytes(2, "big")),           # update: id 2 unknown
+        (0x02, ch(1, 0x011) + (0xFFFF).to_bytes(2, "big") + ch(1, 0x012) + (0x0001).to_bytes(2, "big")),     # Everybody / Default: skipped
+        (0x3A, status), (0x3C, status),                                                     # RfssStatus, AdjacentSite
+        (0x3B, bytes([0x11, wacn >> 12, (wacn >> 4) & 0xFF, ((wacn & 0xF) << 4) | (sysid >> 8), sysid & 0xFF]) + ch(1, 0x155) + bytes([0x70])),
+        (0x39, bytes([0x07, 0x21]) + ch(1, 0x200) + bytes([0x70]) + ch(3, 0x201) + bytes([0x70])),            # AltControl: id 3 unknown
+        (0x2B, bytes([0x01, 0x12, 0x34, 0x07, 0x21]) + (0x00BEEF).to_bytes(3, "big")),       # LocRegResponse
+        (0x2C, bytes([0x20 | (sysid >> 8), sysid & 0xFF]) + (0x123456).to_bytes(3, "big") + (0x654321).to_bytes(3, "big")),
+        (0x2F, bytes([0x00, wacn >> 12, (wacn >> 4) & 0xFF, ((wacn & 0xF) << 4) | (sysid >> 8), sysid & 0xFF]) + (0x00CAFE).to_bytes(3, "big")),
+        (0x15, bytes(8)),                                                                   # unknown opcode: ignored
+    ]
+    lcs = [bytes([0x00, 0x00, 0x00, 0x00, 0x45, 0x67, 0xAB, 0xCD, 0xEF]),                  # GroupVoiceTraffic -> srcUnit
+           bytes([0x02]) + ch(1, 0x030) + (300).to_bytes(2, "big") + ch(1, 0x031) + (301).to_bytes(2, "big"),   # GroupVoiceUpdate
+           bytes([0x23]) + status, bytes([0x0F]) + bytes(8)]
+    return tsbks, lcs
+
+
+def _consumer_events():
+    """The same units as a drained event array (for the Python side) and as `fields` arguments (for the C++ side)."""
+    from p25rx_b200 import EVENT_DTYPE
+    tsbks, lcs = _consumer_units()
+    rows = [(7, tx.make_tsbk(op, 0, pl, last=False)) for op, pl in tsbks]
+    rows.insert(3, (7, tx.make_tsbk(0x00, 0, tsbks[1][1], last=False, bad_crc=True)))       # CRC failure: dropped
+    rows.insert(4, (7, tx.make_tsbk(0x00, 0x90, tsbks[1][1], last=False)))                  # manufacturer-specific: dropped
+    rows += [(3, lcs[0]), (3, lcs[1]), (8, lcs[2]), (8, lcs[3])]
+    ev = np.zeros(len(rows), dtype=EVENT_DTYPE)
+    for i, (k, pl) in enumerate(rows):
+        ev[i]["kind"], ev[i]["sample"], ev[i]["len"] = k, i, len(pl)
+        ev[i]["payload"][: len(pl)] = np.frombuffer(pl, dtype=np.uint8)
+    return ev, [f"{k}:{pl.hex()}" for k, pl in rows]
+
+
+def _parse_consumer(out: str):
+    import json
+    tg = [tuple(int(x) for x in line.split()[1:5]) for line in out.splitlines() if line.startswith("T ")]
+    hub = [(int(line.split()[1]), json.loads(line.split(" ", 2)[2])) for line in out.splitlines() if line.startswith("H ")]
+    return tg, hub
+
+
+def test_cpp_consumer_fields_match_python_adapters():
+    """include/p25cu.hpp TsbkFields / LinkControlFields / fields:: / ChannelParamsMap / RecvConsumer against
+    p25rx_b200/consumers.py on hand-built payloads (no GPU): talkgroups with their traffic-channel frequency and the
+    hub's status JSON, including what must be dropped (bad CRC, manufacturer id, reserved talkgroups, unknown channel ids)."""
+    import json
+    import p25rx_b200
+    from p25rx_b200 import consumers as co
+    p25rx_b200.build()
+    exe = build_host_main()
+    ev, argv = _consumer_events()
+    r = subprocess.run([exe, "fields"] + argv, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    tg, hub = _parse_consumer(r.stdout)
+    ptg, phub = co.consume(ev)
+    assert tg == ptg and [t[2] for t in tg] == [0x4567, 100, 300, 301]
+    assert tg[0][3] == 851_012_500 + 12_500 * 0x123
+    assert hub == [(s, json.loads(j)) for s, j in phub]
+    names = [h[1]["event"] for h in hub]
+    assert names == ["rfssStatus", "adjacentSite", "networkStatus", "altControl", "locReg", "unitReg", "unitDereg", "srcUnit", "rfssStatus"]
+    assert hub[2][1]["payload"] == {"area": 0x11, "wacn": 0xBEE07, "system": 0x2A5}
+    assert hub[1][1]["payload"]["freq"] == 851_012_500 + 12_500 * 0x155 and hub[7][1]["payload"] == 0xABCDEF
+
+
+@pytest.mark.gpu
+def test_cpp_consumer_view_of_decoded_streams(tmp_path):
+    """The consumer view end to end on the GPU path: recordings carrying those TSBKs and link-control words, decoded by
+    the CUDA library; p25host_main's RecvConsumer output must equal consumers.consume() over the Python host layer's
+    events of the same files."""
+    import json
+    import p25rx_b200 as p25
+    from p25rx_b200 import consumers as co
+    exe = build_host_main()
+    tsbks, lcs = _consumer_units()
+    units = []
+    for i in range(0, len(tsbks), 3):
+        grp = tsbks[i:i + 3]
+        units.append(tx.tsdu(0x293, [tx.make_tsbk(op, 0, pl, last=(j == len(grp) - 1)) for j, (op, pl) in enumerate(grp)]))
+    rng = np.random.default_rng(9)
+    voice = [tx.hdu(0x293, bytes(9), 0, 0x80, 0, 0x4567),
+             tx.ldu(0x293, 1, [tx.random_imbe(rng) for _ in range(9)], lcs[0], (1, 2)),
+             tx.ldu(0x293, 2, [tx.random_imbe(rng) for _ in range(9)], bytes(9) + bytes([0x80, 0, 0]), (3, 4)),
+             tx.ldu(0x293, 1, [tx.random_imbe(rng) for _ in range(9)], lcs[1], (5, 6)),
+             tx.tdulc(0x293, lcs[2])]
+    paths = []
+    # stream 1 learns channel id 1 from its own TSDU before the link-control update arrives (one RecvTask per stream)
+    bbs = [tx.baseband_48k(tx.concat_units(us, lead_idle=30, gap_idle=12).dibits, snr_db=22, seed=s)[0]
+           for s, us in enumerate((units, [tx.tsdu(0x293, [tx.make_tsbk(0x3D, 0, _chan_params(1), last=True)])] + voice))]
+    n = max(len(b) for b in bbs)           # replay ends with the shortest recording: pad with an idle carrier
+    for s, bb in enumerate(bbs):
+        bb = np.concatenate([bb, np.zeros(n - len(bb), dtype=np.float32)])
+        path = tmp_path / f"c{s}.f32"
+        with open(path, "wb") as f:
+            co.write_baseband(f, bb)
+        paths.append(str(path))
+    r = subprocess.run([exe, "consumer"] + paths, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    tg, hub = _parse_consumer(r.stdout)
+    rr = p25.ReplayReceiver(n_streams=2)
+    ev = rr.replay([open(pth, "rb") for pth in paths])
+    rr.ctx.close()
+    ev = ev[np.lexsort((ev["sample"], ev["stream"]))]
+    ptg, phub = co.consume(ev)
+    assert tg == ptg and hub == [(s, json.loads(j)) for s, j in phub]
+    assert {t[2] for t in tg} == {0x4567, 100, 300, 301}
+    assert {h[1]["event"] for h in hub} >= {"rfssStatus", "adjacentSite", "networkStatus", "altControl", "locReg", "unitReg", "unitDereg", "srcUnit"}

@@ -63,7 +63,7 @@ def main():
         for chunks in zip(*readers):
             _, power = demod.run_chunk(np.stack(chunks))
             if power is not None:
-                out.write(json.dumps({"event": "sigPower", "dBm": [round(float(x), 2) for x in power]}) + "\n")
+                out.write(json.dumps({"event": "sigPower", "dBm": [round(float(x), 2) if np.isfinite(x) else None for x in power]}) + "\n")
             ctx.decode()
             for e in ctx.poll():
                 out.write(json.dumps(event_json(p25, co, args.files, e)) + "\n")
