@@ -141,8 +141,9 @@ class Workload:
 
     def shift(self, g: int) -> int:
         """Circular shift of global input row g."""
-        n = self.base().shape[1]
-        return (400 * 77 * g) % n if self.kind == "wide" else (g // N_BASE) * 5003 % n
+        b = self.base()
+        n = b.shape[1]
+        return (400 * 77 * g) % n if self.kind == "wide" else (g // len(b)) * 5003 % n      # tile_on_device's rule
 
     def device_input(self, rank: int):
         import torch

@@ -209,8 +209,11 @@ int p25cu_device_baseband(p25cu_ctx* ctx, const float** ptr, size_t* row_stride,
  * sample a few streams of a large batch this way). */
 int p25cu_read_baseband(p25cu_ctx* ctx, uint32_t stream, float* out, size_t n);
 
-/* Channelizer mode only: copy the channel spectra of the last p25cu_demod, [captures][*n_rows][1536] complex float32
- * (48 kS/s per channel, before the channel-select filter), to `out` (nullable: only report *n_rows). */
+/* Channelizer mode only (test hook): while enabled, every p25cu_demod also keeps the channel spectra of its chunk,
+ * c_k[m] = channel k at 48 kS/s AFTER the channel-select filter (the filter is folded into the polyphase prototype, so
+ * no unfiltered spectrum exists on the device).  p25cu_channelizer_output copies them, [captures][*n_rows][1536]
+ * complex float32, to `out` (nullable: only report *n_rows). */
+int p25cu_set_keep_spectra(p25cu_ctx* ctx, int on);
 int p25cu_channelizer_output(p25cu_ctx* ctx, float* out, size_t* n_rows);
 
 /* ---- FEC unit entry points: run the device decoders on caller-provided code words (one word per

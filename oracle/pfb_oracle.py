@@ -63,3 +63,47 @@ def channelize(x: np.ndarray, m0: int = 0, n_out: int | None = None) -> np.ndarr
         u = v[(r + nm) % N]
         out[j] = np.fft.ifft(u) * N                             # sum_q u[q] exp(+2j pi k q / N)
     return out
+
+
+def channel_filter(y: np.ndarray) -> np.ndarray:
+    """The reference's channel-select FIR (src/demod.rs:93) down every channel column of y [n_out][N], zeros before the
+    stream start: c_k[m] = sum_j hc[j] y_k[m - j].  This is what the CUDA kernels deliver as channel spectra: they fold
+    the filter into the polyphase prototype (p25rx_b200/csrc/pfb.cu)."""
+    hc = S.taps_chan().astype(np.float64)
+    y = np.asarray(y, dtype=np.complex128)
+    out = np.zeros_like(y)
+    for j, h in enumerate(hc[: len(y)]):
+        out[j:] += h * y[: len(y) - j]
+    return out
+
+
+def equivalent_prototype() -> np.ndarray:
+    """heq = hp (*) upsample(hc, M): the prototype whose polyphase channelizer output equals channel_filter(channelize(x))."""
+    hp, hc = _taps(), S.taps_chan().astype(np.float64)
+    heq = np.zeros(L + M * (len(hc) - 1), dtype=np.float64)
+    for j, h in enumerate(hc):
+        heq[M * j: M * j + L] += h * hp
+    return heq
+
+
+def channelize_fused(x: np.ndarray, m0: int = 0, n_out: int | None = None) -> np.ndarray:
+    """channel_filter(channelize(x)) computed the way the kernels do: one polyphase pass with the equivalent prototype
+    (15 taps per branch), float32-rounded taps like the device table."""
+    heq = equivalent_prototype()
+    PE = -(-len(heq) // N)
+    h = np.zeros(PE * N)
+    h[: len(heq)] = heq.astype(np.float32).astype(np.float64)
+    h = h.reshape(PE, N)
+    LE = PE * N
+    x = np.asarray(x, dtype=np.complex128)
+    if n_out is None:
+        n_out = len(x) // M - m0
+    xp = np.concatenate([np.zeros(LE, dtype=np.complex128), x])
+    out = np.empty((n_out, N), dtype=np.complex128)
+    r = np.arange(N)
+    for j in range(n_out):
+        nm = M * (m0 + j) + M - 1
+        win = xp[nm + 1: LE + nm + 1][::-1]                     # win[i] = x[nm - i], i = 0 .. LE-1
+        v = np.sum(h * win.reshape(PE, N), axis=0)
+        out[j] = np.fft.ifft(v[(r + nm) % N]) * N
+    return out

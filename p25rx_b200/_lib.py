@@ -25,7 +25,7 @@ assert EVENT_DTYPE.itemsize == 80
 EXPORTS = ["p25cu_create", "p25cu_destroy", "p25cu_last_error", "p25cu_demod", "p25cu_decode", "p25cu_process",
            "p25cu_poll", "p25cu_poll_view", "p25cu_pending", "p25cu_poll_start", "p25cu_poll_packed", "p25cu_unpack_events",
            "p25cu_host_alloc", "p25cu_host_free", "p25cu_host_register", "p25cu_host_unregister", "p25cu_resync", "p25cu_get_stats", "p25cu_cuda_stream", "p25cu_sync", "p25cu_set_overlap",
-           "p25cu_launch_count", "p25cu_demod_timing", "p25cu_device_baseband", "p25cu_read_baseband", "p25cu_channelizer_output", "p25cu_fec_selftest"]
+           "p25cu_launch_count", "p25cu_demod_timing", "p25cu_device_baseband", "p25cu_read_baseband", "p25cu_channelizer_output", "p25cu_set_keep_spectra", "p25cu_fec_selftest"]
 
 
 class Config(C.Structure):
@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
     L.p25cu_demod_timing.argtypes = [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_uint)]
     L.p25cu_device_baseband.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
     L.p25cu_read_baseband.argtypes = [vp, C.c_uint32, vp, sz]
+    L.p25cu_set_keep_spectra.argtypes = [vp, i]
     L.p25cu_channelizer_output.argtypes = [vp, vp, C.POINTER(sz)]
     L.p25cu_fec_selftest.argtypes = [vp, i, vp, sz, i, i, vp, vp]
     _lib = L

@@ -885,6 +885,7 @@ __global__ void __launch_bounds__(K<FMT>::NT) p25_ddc5_fm_kernel(const DdcParams
                 left[r] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int k = P25_TAPS_DECIM - 1; k >= 0; k--) {      // oldest input first
+                    if ((P25_TAPS_DECIM_ZERO_MASK >> k) & 1) continue;  // taps that are zero to working precision
                     const int idx = 5 * r + (P25_TAPS_DECIM - 1) - k;
                     if (idx < 5 * R) own[r] = cfma(c_taps_decim[k], x[idx], own[r]);
                     else left[r] = cfma(c_taps_decim[k], x[idx - 5 * R], left[r]);
@@ -1034,7 +1035,7 @@ constexpr int HROWS = (P25_TAPS_CHAN - 1) / R;        // 10 history rows of the 
 constexpr int DROWS = 3;                    // history rows of the discriminator output (>= 9 samples)
 static_assert((P25_TAPS_CHAN - 1) % R == 0 && DROWS * R >= P25_BOXCAR - 1, "history rows");
 
-template <int FMT>
+template <int FMT, bool MMA = false>
 struct __align__(128) WarpSm {
     unsigned char xs[2][Fmt<FMT>::XBYTES];
     float4 ydA[HROWS + 32], ydB[HROWS + 32];    // row i: (yd[4i], yd[4i+1]) | (yd[4i+2], yd[4i+3])
@@ -1042,10 +1043,38 @@ struct __align__(128) WarpSm {
     unsigned long long full[2];
 };
 
+// Tensor-pipe variant of the channel filter (A/B switch P25CU_DDC5 bit 2; VERDICT r1 item 4 asked for a measurement,
+// not an estimate).  c[j] = sum_k h[k] y[j + 40 - k] over a block of 16 outputs is a [16 x 56] Toeplitz matrix times the
+// block's 56-sample window: seven mma.sync m16n8k8 TF32 steps whose eight columns are (four blocks) x (re, im).  FP32
+// accuracy comes from the split y = hi + lo, h = hi + lo with three products per step (hi hi, hi lo, lo hi; the error
+// is ~2^-21 relative).  The FIR leaves the FP32 pipe (41 of the 66 FFMA2 per output) for the legacy tensor pipe, which
+// pipe_peaks.cu measured at 476 TF32 MAC/clk/SM running beside FFMA2 at 80 % of its own peak.
+//   decimator outputs: two planes (re | im), window index i (0..39 history, 40..163 this iteration, 164..167 ghost)
+//   stored at i + 4 (i >> 4): every B-fragment load (8 columns x 4 rows) then hits 32 different banks.
+constexpr int YPLANE = 208;                     // 168 + 4 * 10 padded window samples per plane; 208 mod 32 = 16
+constexpr int CPAD = 160;                       // channel-filter outputs, o + 4 (o >> 4)
+__device__ __forceinline__ int ypad(int i) { return i + 4 * (i >> 4); }
+template <int FMT>
+struct __align__(128) WarpSm<FMT, true> {
+    unsigned char xs[2][Fmt<FMT>::XBYTES];
+    float y[2][YPLANE];
+    float2 c[CPAD];
+    float4 d4[DROWS + 32];
+    unsigned long long full[2];
+};
+constexpr int ATAB_FLOATS = 7 * 2 * 32 * 4;     // [k-step][hi | lo][lane][a0..a3]
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float4 a, const float b0, const float b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
+                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
 // bulk copy of the slice whose first input has logical index l0 (tail ++ chunk); 32-bit index arithmetic, the slice
 // that still overlaps the carried tail (first iterations of a chunk only) takes the two-copy path
-template <int FMT>
-__device__ __forceinline__ void issue_slice(WarpSm<FMT>& sm, int stage, int ht, int lend, const unsigned char* tail,
+template <int FMT, bool MMA>
+__device__ __forceinline__ void issue_slice(WarpSm<FMT, MMA>& sm, int stage, int ht, int lend, const unsigned char* tail,
                                             const unsigned char* chunk, int l0) {
     constexpr int AL = Fmt<FMT>::AL, ES = Fmt<FMT>::ES, XLEN = Fmt<FMT>::XLEN;
     const int la = l0 & ~(AL - 1);
@@ -1063,19 +1092,39 @@ __device__ __forceinline__ void issue_slice(WarpSm<FMT>& sm, int stage, int ht, 
     if (nc) tma_load_1d(&sm.xs[stage][nt * ES], chunk, nc * ES, &sm.full[stage]);
 }
 
-template <int FMT>
+template <int FMT, bool MMA>
 __global__ void __launch_bounds__(32 * WARPS, Fmt<FMT>::MINB) p25_ddc5_warp_kernel(const DdcParams p, const unsigned its_per_stream,
                                                                              const float dc, const float pw_scale) {
     constexpr int AL = Fmt<FMT>::AL, ES = Fmt<FMT>::ES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSm<FMT>& sm = reinterpret_cast<WarpSm<FMT>*>(smem_raw)[warp];
+    WarpSm<FMT, MMA>& sm = reinterpret_cast<WarpSm<FMT, MMA>*>(smem_raw)[warp];
     if (lane == 0) {
         mbar_init(&sm.full[0], 1);
         mbar_init(&sm.full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = lane; i < HROWS + 32; i += 32) sm.ydA[i] = sm.ydB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    [[maybe_unused]] const float4* atab = nullptr;
+    if constexpr (MMA) {
+        // Toeplitz A fragments of the seven k-steps, split into TF32 hi and lo parts, built once per CTA:
+        // A[i][kk] = h[40 + i - kk] (output row i of the block, window position kk), zero outside the band
+        float* at = reinterpret_cast<float*>(smem_raw + sizeof(WarpSm<FMT, true>) * WARPS);
+        for (int e = threadIdx.x; e < ATAB_FLOATS / 2; e += 32 * WARPS) {
+            const int q = e & 3, ln = (e >> 2) & 31, st = e >> 7;
+            const int row = (ln >> 2) + ((q & 1) ? 8 : 0), kk = 8 * st + (ln & 3) + ((q & 2) ? 4 : 0);
+            const int k = (P25_TAPS_CHAN - 1) + row - kk;
+            const float h = (k >= 0 && k < P25_TAPS_CHAN) ? c_taps_chan[k] : 0.f;
+            const float hi = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
+            at[(st * 2 + 0) * 128 + ln * 4 + q] = hi;
+            at[(st * 2 + 1) * 128 + ln * 4 + q] = h - hi;
+        }
+        atab = reinterpret_cast<const float4*>(at);
+        for (int i = lane; i < 2 * YPLANE; i += 32) (&sm.y[0][0])[i] = 0.f;
+        for (int i = lane; i < CPAD; i += 32) sm.c[i] = make_float2(0.f, 0.f);
+        __syncthreads();
+    } else {
+        for (int i = lane; i < HROWS + 32; i += 32) sm.ydA[i] = sm.ydB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     for (int i = lane; i < DROWS + 32; i += 32) sm.d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 
@@ -1096,8 +1145,8 @@ __global__ void __launch_bounds__(32 * WARPS, Fmt<FMT>::MINB) p25_ddc5_warp_kern
     const unsigned char* chunk = (const unsigned char*)p.iq + s * row_bytes;
     const unsigned char* tail = (const unsigned char*)p.tail_in + s * tail_bytes;
     if (lane == 0) {                                        // warm-up and first stored iteration of the first piece
-        issue_slice<FMT>(sm, 0, ht, lend, tail, chunk, l_base + XNEW * (it_first - 1));
-        issue_slice<FMT>(sm, 1, ht, lend, tail, chunk, l_base + XNEW * it_first);
+        issue_slice<FMT, MMA>(sm, 0, ht, lend, tail, chunk, l_base + XNEW * (it_first - 1));
+        issue_slice<FMT, MMA>(sm, 1, ht, lend, tail, chunk, l_base + XNEW * it_first);
     }
     float2 c_carry = make_float2(0.f, 0.f);
     unsigned use = 0;
@@ -1150,6 +1199,7 @@ __global__ void __launch_bounds__(32 * WARPS, Fmt<FMT>::MINB) p25_ddc5_warp_kern
                 lft[r] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int k = P25_TAPS_DECIM - 1; k >= 0; k--) {
+                    if ((P25_TAPS_DECIM_ZERO_MASK >> k) & 1) continue;  // taps that are zero to working precision (4 of 25)
                     const int idx = 5 * r + (P25_TAPS_DECIM - 1) - k;
                     if (idx < 5 * R) own[r] = cfma(c_taps_decim[k], x[idx], own[r]);
                     else lft[r] = cfma(c_taps_decim[k], x[idx - 5 * R], lft[r]);
@@ -1163,16 +1213,65 @@ __global__ void __launch_bounds__(32 * WARPS, Fmt<FMT>::MINB) p25_ddc5_warp_kern
                 }
             }
         }
-        sm.ydA[HROWS + lane] = make_float4(own[0].x, own[0].y, own[1].x, own[1].y);   // lane 31's row is never read
-        sm.ydB[HROWS + lane] = make_float4(own[2].x, own[2].y, own[3].x, own[3].y);
+        if constexpr (MMA) {                       // window index 40 + 4 lane + r, re and im planes (lane 31: finite ghost values)
+            const int pi = ypad(4 * HROWS + R * lane);
+            *reinterpret_cast<float4*>(&sm.y[0][pi]) = make_float4(own[0].x, own[1].x, own[2].x, own[3].x);
+            *reinterpret_cast<float4*>(&sm.y[1][pi]) = make_float4(own[0].y, own[1].y, own[2].y, own[3].y);
+        } else {
+            sm.ydA[HROWS + lane] = make_float4(own[0].x, own[0].y, own[1].x, own[1].y);   // lane 31's row is never read
+            sm.ydB[HROWS + lane] = make_float4(own[2].x, own[2].y, own[3].x, own[3].y);
+        }
         __syncwarp();                                                                 // S1: xs[stage] consumed, rows visible
         if (lane == 0) {                                    // prefetch two iterations ahead (possibly into the next piece)
-            if (j + 2 < npiece) issue_slice<FMT>(sm, stage, ht, lend, tail, chunk, l_base + XNEW * (it + 2));
-            else if (left) issue_slice<FMT>(sm, stage, ht, lend, tail + tail_bytes, chunk + row_bytes, l_base + XNEW * (j + 1 - npiece));
+            if (j + 2 < npiece) issue_slice<FMT, MMA>(sm, stage, ht, lend, tail, chunk, l_base + XNEW * (it + 2));
+            else if (left) issue_slice<FMT, MMA>(sm, stage, ht, lend, tail + tail_bytes, chunk + row_bytes, l_base + XNEW * (j + 1 - npiece));
         }
 
-        // ---- channel-select FIR: outputs 4 lane + r, window = rows lane .. lane + 10 (44 samples, s = 40 + r - k)
         float2 acc[R];
+        if constexpr (MMA) {
+            // ---- channel-select FIR on the tensor pipe: two D tiles (blocks 0..3 | 4..7) x seven k-steps x three products
+            const int g = lane >> 2, tig = lane & 3;
+            const float* yp = &sm.y[g & 1][0];                       // column n = g: block (g >> 1) of the tile, component g & 1
+            float d0[4] = {dc, dc, dc, dc}, d1[4] = {dc, dc, dc, dc};
+#pragma unroll
+            for (int st = 0; st < 7; st++) {
+                const float4 ah = atab[(2 * st) * 32 + lane], al = atab[(2 * st + 1) * 32 + lane];
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    const int i0 = 16 * (4 * t + (g >> 1)) + 8 * st + tig;      // window sample of B row tig; row tig + 4 is i0 + 4
+                    const float b0 = yp[ypad(i0)], b1 = yp[ypad(i0 + 4)];
+                    const float b0h = __uint_as_float(__float_as_uint(b0) & 0xFFFFE000u), b1h = __uint_as_float(__float_as_uint(b1) & 0xFFFFE000u);
+                    const float b0l = b0 - b0h, b1l = b1 - b1h;
+                    if (t == 0) {
+                        mma_tf32(d0, ah, b0h, b1h);
+                        mma_tf32(d0, ah, b0l, b1l);
+                        mma_tf32(d0, al, b0h, b1h);
+                    } else {
+                        mma_tf32(d1, ah, b0h, b1h);
+                        mma_tf32(d1, ah, b0l, b1l);
+                        mma_tf32(d1, al, b0h, b1h);
+                    }
+                }
+            }
+            // D fragment: (d[0], d[1]) = (re, im) of output 16 (4 t + tig) + g, (d[2], d[3]) of that output + 8
+            {
+                const int o0 = 16 * tig + g, o1 = 64 + 16 * tig + g;
+                sm.c[ypad(o0)] = make_float2(d0[0], d0[1]);
+                sm.c[ypad(o0 + 8)] = make_float2(d0[2], d0[3]);
+                sm.c[ypad(o1)] = make_float2(d1[0], d1[1]);
+                sm.c[ypad(o1 + 8)] = make_float2(d1[2], d1[3]);
+            }
+            __syncwarp();
+            {
+                const float4* cp = reinterpret_cast<const float4*>(&sm.c[ypad(R * lane)]);
+                const float4 v0 = cp[0], v1 = cp[1];
+                acc[0] = make_float2(v0.x, v0.y);
+                acc[1] = make_float2(v0.z, v0.w);
+                acc[2] = make_float2(v1.x, v1.y);
+                acc[3] = make_float2(v1.z, v1.w);
+            }
+        } else {
+        // ---- channel-select FIR: outputs 4 lane + r, window = rows lane .. lane + 10 (44 samples, s = 40 + r - k)
 #pragma unroll
         for (int r = 0; r < R; r++) acc[r] = make_float2(dc, dc);
 #pragma unroll
@@ -1187,6 +1286,7 @@ __global__ void __launch_bounds__(32 * WARPS, Fmt<FMT>::MINB) p25_ddc5_warp_kern
                     if (k >= 0 && k < P25_TAPS_CHAN) acc[r] = cfma(c_taps_chan[k], xs4[q], acc[r]);
                 }
             }
+        }
         }
         // ---- FM discriminator on the four outputs in registers; the sample before comes from the lane below
         float2 prev;
@@ -1233,13 +1333,20 @@ __global__ void __launch_bounds__(32 * WARPS, Fmt<FMT>::MINB) p25_ddc5_warp_kern
         }
         // ---- roll the histories: the last 10 decimator rows and 3 discriminator rows move to the front
         float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra, rd = ra;
-        if (lane < HROWS) {
+        if constexpr (MMA) {                       // window samples 124 .. 163 -> 0 .. 39 in both planes (padded indices differ)
+            if (lane < 20) {
+                const int src = NOUT + 4 * (lane >> 1), pl = lane & 1;
+                ra = make_float4(sm.y[pl][ypad(src)], sm.y[pl][ypad(src + 1)], sm.y[pl][ypad(src + 2)], sm.y[pl][ypad(src + 3)]);
+            }
+        } else if (lane < HROWS) {
             ra = sm.ydA[31 + lane];
             rb = sm.ydB[31 + lane];
         }
         if (lane < DROWS) rd = sm.d4[31 + lane];
         __syncwarp();                                                                 // S3
-        if (lane < HROWS) {
+        if constexpr (MMA) {
+            if (lane < 20) *reinterpret_cast<float4*>(&sm.y[lane & 1][ypad(4 * (lane >> 1))]) = ra;
+        } else if (lane < HROWS) {
             sm.ydA[lane] = ra;
             sm.ydB[lane] = rb;
         }
@@ -1332,11 +1439,11 @@ static cudaError_t launch_fast5(const DdcParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-template <int FMT>
+template <int FMT, bool MMA>
 static cudaError_t launch_w5(const DdcParams& p, cudaStream_t st) {
-    auto kern = w5::p25_ddc5_warp_kernel<FMT>;
-    const size_t smem = sizeof(w5::WarpSm<FMT>) * w5::WARPS;
-    const int grid_max = p.plan->grid_w5[FMT];
+    auto kern = w5::p25_ddc5_warp_kernel<FMT, MMA>;
+    const size_t smem = sizeof(w5::WarpSm<FMT, MMA>) * w5::WARPS + (MMA ? w5::ATAB_FLOATS * sizeof(float) : 0);
+    const int grid_max = MMA ? p.plan->grid_w5m[FMT] : p.plan->grid_w5[FMT];
     const unsigned ips = (p.n_out + w5::NOUT - 1) / w5::NOUT;
     const unsigned long long total = (unsigned long long)p.n_streams * ips;
     unsigned long long want = (total + 3) / 4;                 // at least ~4 iterations per warp (one warm-up each)
@@ -1373,8 +1480,11 @@ cudaError_t p25cu_ddc_plan_device(P25DevPlan* plan) {
     }
     if ((e = plan_one(fast5::p25_ddc5_fm_kernel<U8>, fast5::K<U8>::NT, sizeof(fast5::Smem<U8>), n_sm, &plan->grid_fast5[U8])) != cudaSuccess) return e;
     if ((e = plan_one(fast5::p25_ddc5_fm_kernel<CF>, fast5::K<CF>::NT, sizeof(fast5::Smem<CF>), n_sm, &plan->grid_fast5[CF])) != cudaSuccess) return e;
-    if ((e = plan_one(w5::p25_ddc5_warp_kernel<U8>, 32 * w5::WARPS, sizeof(w5::WarpSm<U8>) * w5::WARPS, n_sm, &plan->grid_w5[U8])) != cudaSuccess) return e;
-    if ((e = plan_one(w5::p25_ddc5_warp_kernel<CF>, 32 * w5::WARPS, sizeof(w5::WarpSm<CF>) * w5::WARPS, n_sm, &plan->grid_w5[CF])) != cudaSuccess) return e;
+    if ((e = plan_one(w5::p25_ddc5_warp_kernel<U8, false>, 32 * w5::WARPS, sizeof(w5::WarpSm<U8>) * w5::WARPS, n_sm, &plan->grid_w5[U8])) != cudaSuccess) return e;
+    if ((e = plan_one(w5::p25_ddc5_warp_kernel<CF, false>, 32 * w5::WARPS, sizeof(w5::WarpSm<CF>) * w5::WARPS, n_sm, &plan->grid_w5[CF])) != cudaSuccess) return e;
+    const size_t atab = w5::ATAB_FLOATS * sizeof(float);
+    if ((e = plan_one(w5::p25_ddc5_warp_kernel<U8, true>, 32 * w5::WARPS, sizeof(w5::WarpSm<U8, true>) * w5::WARPS + atab, n_sm, &plan->grid_w5m[U8])) != cudaSuccess) return e;
+    if ((e = plan_one(w5::p25_ddc5_warp_kernel<CF, true>, 32 * w5::WARPS, sizeof(w5::WarpSm<CF, true>) * w5::WARPS + atab, n_sm, &plan->grid_w5m[CF])) != cudaSuccess) return e;
     // the generic kernels' shared memory (27 - 72 KB) needs the opt-in as well
     if ((e = cudaFuncSetAttribute(p25_ddc_fm_kernel<true, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<true>))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(p25_ddc_fm_kernel<true, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<true>))) != cudaSuccess) return e;
@@ -1382,7 +1492,8 @@ cudaError_t p25cu_ddc_plan_device(P25DevPlan* plan) {
     return cudaFuncSetAttribute(p25_ddc_fm_kernel<false, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<false>));
 }
 
-// /5 fast paths: bit 0 = warp-autonomous kernel for u8, bit 1 = for cf32 (otherwise the tile kernel); A/B switch P25CU_DDC5
+// /5 fast paths: bit 0 = warp-autonomous kernel for u8, bit 1 = for cf32 (otherwise the tile kernel), bit 2 = its channel
+// filter on the tensor pipe; A/B switch P25CU_DDC5
 static int ddc5_variant() {
     static const int v = getenv("P25CU_DDC5") ? atoi(getenv("P25CU_DDC5")) : 3;
     return v;
@@ -1391,8 +1502,11 @@ static int ddc5_variant() {
 cudaError_t p25cu_launch_ddc(const DdcParams& p, int format, int decimation, cudaStream_t st) {
     if (p.n_out == 0 && p.n == 0) return cudaSuccess;
     if (decimation == 5 && p.aligned16 && p.n_out > 0 && p.a0 >= p.ht && p.n >= p.ht && p.ht == (unsigned)Cfg<false>::HT) {
-        if (format == P25CU_FMT_U8_IQ && (ddc5_variant() & 1)) return launch_w5<P25CU_FMT_U8_IQ>(p, st);
-        if (format == P25CU_FMT_CF32_IQ && (ddc5_variant() & 2)) return launch_w5<P25CU_FMT_CF32_IQ>(p, st);
+        const bool mma = (ddc5_variant() & 4) != 0;     // channel filter on the tensor pipe (mma.sync 3xTF32)
+        if (format == P25CU_FMT_U8_IQ && (ddc5_variant() & 1))
+            return mma ? launch_w5<P25CU_FMT_U8_IQ, true>(p, st) : launch_w5<P25CU_FMT_U8_IQ, false>(p, st);
+        if (format == P25CU_FMT_CF32_IQ && (ddc5_variant() & 2))
+            return mma ? launch_w5<P25CU_FMT_CF32_IQ, true>(p, st) : launch_w5<P25CU_FMT_CF32_IQ, false>(p, st);
     }
     // /5 fast path: aligned rows, the whole history inside the stream (no implicit zeros), chunk at least one tail long
     if (decimation == 5 && p.aligned16 && p.n_out > 0 && p.a0 >= p.ht && p.n >= p.ht && p.ht == (unsigned)Cfg<false>::HT)

@@ -22,10 +22,10 @@ unsigned p25cu_pfb_channels();
 unsigned p25cu_pfb_decimation();
 unsigned p25cu_pfb_hist_rows();
 cudaError_t p25cu_pfb_upload(float** d_taps, float2** d_twiddle);
-cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out, const float* taps, const float2* twiddle, float2* y,
-                             unsigned y_rows, float* bb, size_t row_stride, float* power_sum, unsigned long long a0,
-                             unsigned long long m0, unsigned n, unsigned n_out, unsigned n_captures, cudaStream_t st,
-                             unsigned* launches, const P25DevPlan* plan);
+cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out, const float* taps, const float2* twiddle, float* d,
+                             unsigned d_rows, float2* y, unsigned y_rows, float* bb, size_t row_stride, float* power_sum,
+                             unsigned long long a0, unsigned long long m0, unsigned n, unsigned n_out, unsigned n_captures,
+                             cudaStream_t st, unsigned* launches, const P25DevPlan* plan);
 
 // Per-device launch plans (P25DevPlan): filled once per device, under a mutex, by the first context created on it.
 static std::mutex g_plan_mu;
@@ -87,9 +87,12 @@ struct p25cu_ctx {
     unsigned n_captures;       // 0 = one stream per input row
     float* d_pfb_taps;
     float2* d_twiddle;
-    float2* d_y;               // [captures][y_rows][1536] channel spectra, time-major
-    float2* d_ytmp;            // [captures][hist][1536] staging for the carried history rows
+    float* d_d;                // [captures][d_rows][1536] discriminator output, time-major: 9 carried rows | this chunk
+    float* d_dtmp;             // [captures][9][1536] staging for the carried rows
+    unsigned d_rows;
+    float2* d_y;               // [captures][y_rows][1536] channel-filtered spectra of the last chunk (test hook, lazy)
     unsigned y_rows;
+    int keep_spectra;
 };
 
 static thread_local char g_create_err[512] = "";
@@ -135,8 +138,9 @@ extern "C" void p25cu_destroy(p25cu_ctx* ctx) {
     cudaFree(ctx->d_golay);
     cudaFree(ctx->d_pfb_taps);
     cudaFree(ctx->d_twiddle);
+    cudaFree(ctx->d_d);
+    cudaFree(ctx->d_dtmp);
     cudaFree(ctx->d_y);
-    cudaFree(ctx->d_ytmp);
     cudaFreeHost(ctx->h_events);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_bb_ready[i]) cudaEventDestroy(ctx->ev_bb_ready[i]);
@@ -217,10 +221,11 @@ static int create_impl(p25cu_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->d_tail[1], 0, tail_rows * ctx->ht * sizeof(float2), ctx->stream));
     if (wide) {
         const size_t ch = p25cu_pfb_channels(), hist = p25cu_pfb_hist_rows();
-        ctx->y_rows = (unsigned)(hist + ctx->max_out);
-        CK(cudaMalloc(&ctx->d_y, (size_t)ctx->n_captures * ctx->y_rows * ch * sizeof(float2)));
-        CK(cudaMemsetAsync(ctx->d_y, 0, (size_t)ctx->n_captures * ctx->y_rows * ch * sizeof(float2), ctx->stream));
-        CK(cudaMalloc(&ctx->d_ytmp, (size_t)ctx->n_captures * hist * ch * sizeof(float2)));
+        ctx->d_rows = (unsigned)(hist + ctx->max_out);
+        ctx->y_rows = (unsigned)ctx->max_out;
+        CK(cudaMalloc(&ctx->d_d, (size_t)ctx->n_captures * ctx->d_rows * ch * sizeof(float)));
+        CK(cudaMemsetAsync(ctx->d_d, 0, (size_t)ctx->n_captures * ctx->d_rows * ch * sizeof(float), ctx->stream));
+        CK(cudaMalloc(&ctx->d_dtmp, (size_t)ctx->n_captures * hist * ch * sizeof(float)));
         CK(p25cu_pfb_upload(&ctx->d_pfb_taps, &ctx->d_twiddle));
     }
     for (int i = 0; i < 2; i++) {
@@ -358,17 +363,19 @@ extern "C" int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_d
     const bool timed = ctx->timing && n && ctx->n_timed < 128;
     if (timed) CK(cudaEventRecord(ctx->tev[2 * ctx->n_timed], ctx->stream));
     if (n && ctx->n_captures) {
-        // wideband capture -> 1,536 channels per capture (pfb.cu): spectra, per-channel baseband, carried state
+        // wideband capture -> 1,536 channels per capture (pfb.cu): discriminator rows, per-channel baseband, carried state
         const size_t ch = p25cu_pfb_channels(), hist = p25cu_pfb_hist_rows();
         unsigned nl = 0;
-        CK(p25cu_launch_pfb(d_in, p.tail_in, p.tail_out, ctx->d_pfb_taps, ctx->d_twiddle, ctx->d_y, ctx->y_rows, p.bb, p.row_stride,
-                            p.power_sum, p.a0, p.m0, p.n, p.n_out, ctx->n_captures, ctx->stream, &nl, ctx->plan));
+        if (ctx->keep_spectra && !ctx->d_y) CK(cudaMalloc(&ctx->d_y, (size_t)ctx->n_captures * ctx->y_rows * ch * sizeof(float2)));
+        CK(p25cu_launch_pfb(d_in, p.tail_in, p.tail_out, ctx->d_pfb_taps, ctx->d_twiddle, ctx->d_d, ctx->d_rows,
+                            ctx->keep_spectra ? ctx->d_y : nullptr, ctx->y_rows, p.bb, p.row_stride, p.power_sum, p.a0, p.m0, p.n, p.n_out,
+                            ctx->n_captures, ctx->stream, &nl, ctx->plan));
         ctx->launches += nl;
-        if (p.n_out) {   // the last `hist` rows of (history ++ this chunk) become the next chunk's history
-            const size_t row = ch * sizeof(float2);
-            CK(cudaMemcpy2DAsync(ctx->d_ytmp, hist * row, ctx->d_y + (size_t)p.n_out * ch, (size_t)ctx->y_rows * row, hist * row,
+        if (p.n_out) {   // the last `hist` rows of (carried rows ++ this chunk) become the next chunk's carried rows
+            const size_t row = ch * sizeof(float);
+            CK(cudaMemcpy2DAsync(ctx->d_dtmp, hist * row, ctx->d_d + (size_t)p.n_out * ch, (size_t)ctx->d_rows * row, hist * row,
                                  ctx->n_captures, cudaMemcpyDeviceToDevice, ctx->stream));
-            CK(cudaMemcpy2DAsync(ctx->d_y, (size_t)ctx->y_rows * row, ctx->d_ytmp, hist * row, hist * row, ctx->n_captures,
+            CK(cudaMemcpy2DAsync(ctx->d_d, (size_t)ctx->d_rows * row, ctx->d_dtmp, hist * row, hist * row, ctx->n_captures,
                                  cudaMemcpyDeviceToDevice, ctx->stream));
         }
         ctx->tail_cur ^= 1;
@@ -750,19 +757,29 @@ extern "C" int p25cu_read_baseband(p25cu_ctx* ctx, uint32_t stream, float* out, 
     return P25CU_OK;
 }
 
+extern "C" int p25cu_set_keep_spectra(p25cu_ctx* ctx, int on) {
+    if (!ctx) return P25CU_ERR_ARG;
+    if (!ctx->n_captures) {
+        snprintf(ctx->err, sizeof ctx->err, "p25cu_set_keep_spectra: context is not in channelizer mode (decimation 400)");
+        return P25CU_ERR_STATE;
+    }
+    ctx->keep_spectra = on ? 1 : 0;
+    return P25CU_OK;
+}
+
 extern "C" int p25cu_channelizer_output(p25cu_ctx* ctx, float* out, size_t* n_rows) {
     if (!ctx || !n_rows) return P25CU_ERR_ARG;
-    if (!ctx->n_captures) {
-        snprintf(ctx->err, sizeof ctx->err, "p25cu_channelizer_output: context is not in channelizer mode (decimation 400)");
+    if (!ctx->n_captures || !ctx->keep_spectra || !ctx->d_y) {
+        snprintf(ctx->err, sizeof ctx->err, "p25cu_channelizer_output: needs channelizer mode (decimation 400) and "
+                 "p25cu_set_keep_spectra(ctx, 1) before the p25cu_demod whose spectra are wanted");
         return P25CU_ERR_STATE;
     }
     CK(cudaSetDevice(ctx->cfg.device));
     *n_rows = ctx->last_n_out;
     if (out && ctx->last_n_out) {
-        // the carried history (rows 0..63) was refreshed after the chunk, so this chunk's rows start at row `hist` unchanged
         const size_t ch = p25cu_pfb_channels(), row = ch * sizeof(float2);
-        CK(cudaMemcpy2DAsync(out, ctx->last_n_out * row, ctx->d_y + (size_t)p25cu_pfb_hist_rows() * ch, (size_t)ctx->y_rows * row,
-                             ctx->last_n_out * row, ctx->n_captures, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpy2DAsync(out, ctx->last_n_out * row, ctx->d_y, (size_t)ctx->y_rows * row, ctx->last_n_out * row, ctx->n_captures,
+                             cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return P25CU_OK;

@@ -84,7 +84,8 @@ struct P25DevPlan {
     int grid_ddc50;               // persistent grid of fast::p25_ddc_fm_stream_kernel
     int grid_ddc50_u8;            // ... of its u8 instantiation
     int grid_fast5[2];            // fast5::p25_ddc5_fm_kernel<FMT>
-    int grid_w5[2];               // w5::p25_ddc5_warp_kernel<FMT>
+    int grid_w5[2];               // w5::p25_ddc5_warp_kernel<FMT, false>
+    int grid_w5m[2];              // ... with the channel filter on the tensor pipe
     int pfb_slots;                // resident CTAs of the channelizer kernel
 };
 

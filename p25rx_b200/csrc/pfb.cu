@@ -16,14 +16,9 @@
 //   v_m[r] = sum_{p<4} h[r + 1536 p] x[n_m - r - 1536 p]           (4 complex-by-real taps per branch)
 //   y_k[m] = sum_q v_m[(q + n_m) mod 1536] exp(+2j pi k q / 1536)   (one 1,536-point inverse DFT per output time)
 //
-// Kernel A (p25_pfb_kernel): a CTA owns a run of consecutive output times; for each it forms the branches from the
-// input window in global memory (consecutive windows overlap by 93 %: L1/L2 hits) and runs the DFT as a mixed-radix
-// Stockham FFT 3 x 8 x 8 x 8 in shared memory (radix-8 butterflies in registers, twiddles from a 1,536-entry table);
-// the last pass writes the spectrum time-major, Y[m][k], fully coalesced.
-// Kernel B (p25_chan_fm_kernel): a CTA takes 32 channels x 128 output times of Y (256-byte row segments, lanes =
-// channels), runs the channel filter as a sliding register window down each lane's column, the discriminator
-// and the boxcar, and transposes through shared memory so that every channel's baseband row is written in
-// 128-byte segments.  HBM-bound: 8 B in + 2 x 30.7 B (Y out, Y in) + 15.4 B out per input sample.
+// Round 2 folds the channel-select FIR into the prototype (see kernel A below): kernel A = polyphase branches + FFT +
+// discriminator, kernel B = boxcar + transpose.  Algorithmic HBM traffic: 8 B per input sample in, 4 B per channel and
+// output time out (15.4 B per input sample); the discriminator rows between the two kernels add 2 x 15.4 B.
 #include "p25cu_internal.cuh"
 #include "p25_pfb_taps.h"
 
@@ -32,15 +27,6 @@ namespace pfb {
 constexpr int N = P25_PFB_N, M = P25_PFB_M, P = P25_PFB_P, L = N * P;
 constexpr int NT = 256;
 static_assert(N == 3 * 8 * 8 * 8, "FFT plan is 3 x 8 x 8 x 8");
-
-// Shared memory holds only the FFT ping-pong buffers and the twiddles (37 KB -> 6 CTAs per SM).  The input window
-// (6,144 samples per output time, 93 % of it shared with the previous output time of the same CTA) is read straight
-// from global memory: the re-reads hit L1/L2, and the occupancy this buys matters more than the staging it saves
-// (staged window: 2 CTAs per SM, 23 % issue utilisation).
-struct SmemA {
-    float2 fa[N], fb[N];
-    float2 tw[N];
-};
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -80,120 +66,6 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
     v[7] = csub(E3, T3);
 }
 
-// one radix-8 Stockham pass: thread j of 192, NS = product of the radices already done
-template <int NS, bool LAST>
-__device__ __forceinline__ void pass8(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ tw, int j) {
-    const int k = j % NS;
-    float2 v[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) v[r] = in[j + r * (N / 8)];
-#pragma unroll
-    for (int r = 1; r < 8; r++) v[r] = cmul(v[r], tw[r * k * (N / (NS * 8))]);
-    dft8(v);
-    const int j0 = (j / NS) * NS * 8 + k;
-#pragma unroll
-    for (int r = 0; r < 8; r++) out[j0 + r * NS] = v[r];
-}
-
-struct PfbParams {
-    const float2* iq;          // [captures][n]
-    const float2* tail_in;     // [captures][L]
-    const float* taps;         // [L] prototype
-    const float2* twiddle;     // [N] exp(+2 pi i t / N)
-    float2* y;                 // [captures][y_rows][N], this chunk's rows start at row hist
-    unsigned long long a0, m0; // absolute input / output index of the chunk start
-    unsigned n, n_out, n_captures;
-    unsigned y_rows, hist;
-};
-
-__global__ void __launch_bounds__(NT) p25_pfb_kernel(const PfbParams p, const unsigned times_per_cta) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemA& sm = *reinterpret_cast<SmemA*>(smem_raw);
-    const int tid = threadIdx.x;
-    const unsigned cap = blockIdx.y;
-    const unsigned t_first = blockIdx.x * times_per_cta;         // this CTA's consecutive output times, relative to m0
-    const unsigned t_last = min(t_first + times_per_cta, p.n_out);
-    const float2* chunk = p.iq + (size_t)cap * p.n;
-    const float2* tail = p.tail_in + (size_t)cap * L;
-    for (int i = tid; i < N; i += NT) sm.tw[i] = p.twiddle[i];
-    float2* yc = p.y + ((size_t)cap * p.y_rows + p.hist) * N;
-    __syncthreads();
-
-    for (unsigned tr = t_first; tr < t_last; tr++) {
-        // newest input of output m (absolute) is n_m = M m + M - 1; its logical index in (tail ++ chunk) is e
-        const long long n_m = (long long)M * ((long long)p.m0 + tr) + (M - 1);
-        const long long e = n_m - (long long)p.a0 + L;           // tail holds L samples
-        const int nm_mod = (int)((unsigned long long)n_m % N);
-        const bool in_chunk = e - (L - 1) >= L;                  // the whole window lies in this chunk
-        // branches: v[r] = sum_p h[r + N p] * x[n_m - r - N p], stored at q = (r - n_m) mod N
-#pragma unroll
-        for (int jr = 0; jr < N / NT; jr++) {
-            const int r = tid + jr * NT;
-            float2 acc = make_float2(0.f, 0.f);
-            if (in_chunk) {
-                const float2* x = chunk + (e - L - r);
-#pragma unroll
-                for (int pp = 0; pp < P; pp++) acc = cfma(__ldg(p.taps + r + N * pp), __ldg(x - N * pp), acc);
-            } else {
-#pragma unroll
-                for (int pp = 0; pp < P; pp++) {
-                    const long long l = e - r - N * pp;
-                    float2 xv = make_float2(0.f, 0.f);
-                    if (l >= L) xv = __ldg(chunk + (l - L));
-                    else if (l >= 0) xv = tail[l];
-                    acc = cfma(__ldg(p.taps + r + N * pp), xv, acc);
-                }
-            }
-            int q = r - nm_mod;
-            if (q < 0) q += N;
-            sm.fa[q] = acc;
-        }
-        __syncthreads();
-        // radix-3 pass (NS = 1): 512 butterflies
-        for (int j = tid; j < N / 3; j += NT) {
-            const float2 a = sm.fa[j], b = sm.fa[j + N / 3], c = sm.fa[j + 2 * (N / 3)];
-            const float s3 = 0.86602540378443865f;
-            const float2 bc = cadd(b, c), d = csub(b, c);
-            const float2 mid = make_float2(a.x - 0.5f * bc.x, a.y - 0.5f * bc.y);
-            const float2 rot = make_float2(-s3 * d.y, s3 * d.x);          // i * s3 * (b - c)
-            sm.fb[3 * j] = cadd(a, bc);
-            sm.fb[3 * j + 1] = cadd(mid, rot);                             // a + b w + c w^2, w = exp(+2 pi i / 3)
-            sm.fb[3 * j + 2] = csub(mid, rot);
-        }
-        __syncthreads();
-        if (tid < N / 8) pass8<3, false>(sm.fb, sm.fa, sm.tw, tid);
-        __syncthreads();
-        if (tid < N / 8) pass8<24, false>(sm.fa, sm.fb, sm.tw, tid);
-        __syncthreads();
-        if (tid < N / 8) pass8<192, true>(sm.fb, yc + (size_t)tr * N, sm.tw, tid);   // natural order, straight to HBM
-        __syncthreads();                                         // fb is read until here; fa is rewritten next
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ kernel B
-constexpr int KC = 32;                 // channels per CTA
-constexpr int TB = 128;                // output times per CTA
-constexpr int HC = P25_TAPS_CHAN - 1;  // 40
-constexpr int HALO = HC + 1 + (P25_BOXCAR - 1);   // 50
-constexpr int RC = 6;
-
-struct SmemB {
-    float2 yt[TB + HALO][KC];
-    float2 ct[TB + 10 + RC][KC];
-    float dt[TB + 9][KC + 1];
-    float pw[KC];
-};
-
-__constant__ float c_chan[P25_TAPS_CHAN];
-
-struct ChanParams {
-    const float2* y;           // [captures][y_rows][N]
-    float* bb;                 // baseband rows, stream = capture * N + channel
-    size_t row_stride;
-    float* power_sum;          // [streams] or null
-    unsigned n_out, n_captures, y_rows, hist;
-};
-
 __device__ __forceinline__ float atan2_branchfree(float y, float x) {   // same polynomial as ddc_fm.cu disc_atan2
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
@@ -214,55 +86,215 @@ __device__ __forceinline__ float atan2_branchfree(float y, float x) {   // same 
     return copysignf(r, y);
 }
 
-__global__ void __launch_bounds__(256) p25_chan_fm_kernel(const ChanParams p) {
+// ------------------------------------------------------------------------------------------------ kernel A
+// Round 2: the per-channel channel-select FIR (41 taps at 48 kS/s, src/demod.rs:93) is folded into the prototype.
+// Channel k after the channel filter is
+//     c_k[m] = sum_j hc[j] y_k[m - j] = sum_i heq[i] x[n_m - i] exp(-2j pi k (n_m - i) / N),
+//     heq = hp (*) upsample(hc, M)           (6,144 + 40 * 400 = 22,144 taps, zero-padded to PE * N = 23,040)
+// i.e. the same polyphase form with PE = 15 taps per branch instead of 4 -- 23,040 complex-by-real MACs per output time
+// for all 1,536 channels, instead of 6,144 + 1,536 * 41 = 69,120 -- and no [time][channel] spectra round trip through HBM
+// before the FIR (the round-1 design moved 61 bytes per input sample there).
+//
+// A CTA (512 threads, one per SM: 222 KB of shared memory) owns a run of consecutive output times of one capture:
+//   * the input window lives in a shared-memory ring of 16 x 1,536 samples (192 KB) indexed by the logical sample
+//     index (carried tail ++ chunk); every output time brings M = 400 new samples, prefetched one step ahead;
+//   * a thread owns three polyphase branches r = tid + 512 b and keeps their 45 prototype taps in registers for the
+//     whole run, so the branch sums cost one LDS.64 + one FFMA2 per tap;
+//   * the 1,536-point inverse DFT is the mixed-radix Stockham FFT 3 x 8 x 8 x 8 in shared memory; its last pass leaves
+//     every thread with the same eight channels at every output time, so the previous c_k[m - 1] stays in registers and
+//     the FM discriminator (src/demod.rs:109-111) runs right there: only d_k[m] (4 bytes per channel and time) goes to
+//     HBM, time-major; power (src/demod.rs:95-101) accumulates in registers;
+//   * one warm-up output time per run supplies c_k[m0 - 1].
+// Kernel B then only applies the 10-tap boxcar (src/demod.rs:114) along time and transposes into the baseband rows.
+constexpr int PE = 15;                 // taps per branch of the equivalent prototype
+constexpr int LE = N * PE;             // 23,040
+constexpr int HTX = 23552;             // carried input tail (>= LE + M - 1, a multiple of 128)
+constexpr int RROWS = 16, RING = RROWS * N;
+constexpr int NTX = 512;
+constexpr int DHIST = P25_BOXCAR - 1;  // discriminator rows carried in front of every chunk (9)
+static_assert(HTX >= LE + M - 1 && RING >= LE + 2 * M, "window + prefetch must fit");
+
+struct SmemX {
+    float2 ring[RING];
+    float2 fa[N], fb[N];
+    float2 tw[N / 2];                  // exp(+2 pi i t / N), t < N / 2; the other half is its negative
+};
+
+struct PfbParams {
+    const float2* iq;          // [captures][n]
+    const float2* tail_in;     // [captures][HTX]
+    const float* taps;         // [LE] equivalent prototype (prototype (*) upsampled channel filter)
+    const float2* twiddle;     // [N] exp(+2 pi i t / N)
+    float* d;                  // [captures][d_rows][N] discriminator output, time-major; this chunk's rows start at DHIST
+    float2* y;                 // nullable: [captures][y_rows][N] channel-filtered spectra c_k[m] of this chunk (test hook)
+    float* power_sum;          // nullable: [captures * N]
+    unsigned long long a0, m0; // absolute input / output index of the chunk start
+    unsigned n, n_out, n_captures;
+    unsigned d_rows, y_rows;
+};
+
+__device__ __forceinline__ float2 load_logical(const PfbParams& p, const float2* tail, const float2* chunk, long long l) {
+    if (l < HTX) return l >= 0 ? tail[l] : make_float2(0.f, 0.f);
+    const long long i = l - HTX;
+    return i < (long long)p.n ? __ldg(chunk + i) : make_float2(0.f, 0.f);
+}
+__device__ __forceinline__ float2 twid(const float2* tw, int t) {   // t in [0, N)
+    const float2 w = tw[t < N / 2 ? t : t - N / 2];
+    return t < N / 2 ? w : make_float2(-w.x, -w.y);
+}
+
+// one radix-8 Stockham pass with the half twiddle table
+template <int NS>
+__device__ __forceinline__ void pass8x(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ tw, int j) {
+    const int k = j % NS;
+    float2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = in[j + r * (N / 8)];
+#pragma unroll
+    for (int r = 1; r < 8; r++) v[r] = cmul(v[r], twid(tw, r * k * (N / (NS * 8))));
+    dft8(v);
+    const int j0 = (j / NS) * NS * 8 + k;
+#pragma unroll
+    for (int r = 0; r < 8; r++) out[j0 + r * NS] = v[r];
+}
+
+__global__ void __launch_bounds__(NTX, 1) p25_pfbx_kernel(const PfbParams p, const unsigned times_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemB& sm = *reinterpret_cast<SmemB*>(smem_raw);
+    SmemX& sm = *reinterpret_cast<SmemX*>(smem_raw);
+    const int tid = threadIdx.x;
+    const unsigned cap = blockIdx.y;
+    const int t_first = (int)(blockIdx.x * times_per_cta);       // this CTA's consecutive output times, relative to m0
+    const int t_last = min(t_first + (int)times_per_cta, (int)p.n_out);
+    if (t_first >= t_last) return;
+    const float2* chunk = p.iq + (size_t)cap * p.n;
+    const float2* tail = p.tail_in + (size_t)cap * HTX;
+    for (int i = tid; i < N / 2; i += NTX) sm.tw[i] = p.twiddle[i];
+    float tap[3][PE];
+#pragma unroll
+    for (int b = 0; b < 3; b++)
+#pragma unroll
+        for (int pp = 0; pp < PE; pp++) tap[b][pp] = __ldg(p.taps + tid + NTX * b + N * pp);
+    // logical index (tail ++ chunk, tail = HTX samples) of the newest input of output time t: n_m - a0 + HTX
+    const long long e_base = (long long)M * (long long)p.m0 + (M - 1) - (long long)p.a0 + HTX;
+    {   // the window of the warm-up output time t_first - 1
+        const long long e0 = e_base + (long long)M * (t_first - 1);
+        for (int i = tid; i < LE; i += NTX) {
+            const long long l = e0 - (LE - 1) + i;
+            sm.ring[(int)((l + 4ll * RING) % RING)] = load_logical(p, tail, chunk, l);
+        }
+    }
+    float2 nx = make_float2(0.f, 0.f);                            // next output time's new samples, one per thread (M <= NTX)
+    if (tid < M) nx = load_logical(p, tail, chunk, e_base + (long long)M * (t_first - 1) + 1 + tid);
+    float2 cprev[8];
+    float pw[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        cprev[r] = make_float2(0.f, 0.f);
+        pw[r] = 0.f;
+    }
+    float* dcap = p.d + ((size_t)cap * p.d_rows + DHIST) * N;
+
+    for (int t = t_first - 1; t < t_last; t++) {
+        __syncthreads();                                          // ring holds the window of t; fa / fb are free
+        const long long e = e_base + (long long)M * t;            // > LE by construction (HTX >= LE + M - 1)
+        const long long n_m = (long long)M * ((long long)p.m0 + t) + (M - 1);
+        const int nm_mod = (int)(((n_m % N) + N) % N);
+        // branches: v[r] = sum_p heq[r + N p] * x[n_m - r - N p], stored at q = (r - n_m) mod N
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            const int r = tid + NTX * b;
+            const unsigned J = (unsigned)(e - r);
+            const unsigned row0 = J / N, col = J - row0 * N;
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int pp = 0; pp < PE; pp++) acc = cfma(tap[b][pp], sm.ring[((row0 - pp) & (RROWS - 1)) * N + col], acc);
+            int q = r - nm_mod;
+            if (q < 0) q += N;
+            sm.fa[q] = acc;
+        }
+        __syncthreads();                                          // window consumed, fa complete
+        if (tid < M && t + 1 < t_last) sm.ring[(int)((e + 1 + tid) % RING)] = nx;     // slots older than the next window
+        if (tid < M && t + 2 < t_last) nx = load_logical(p, tail, chunk, e + M + 1 + tid);
+        // radix-3 pass (NS = 1): 512 butterflies, one per thread
+        {
+            const int j = tid;
+            const float2 a = sm.fa[j], bb = sm.fa[j + N / 3], c = sm.fa[j + 2 * (N / 3)];
+            const float s3 = 0.86602540378443865f;
+            const float2 bc = cadd(bb, c), dd = csub(bb, c);
+            const float2 mid = make_float2(a.x - 0.5f * bc.x, a.y - 0.5f * bc.y);
+            const float2 rot = make_float2(-s3 * dd.y, s3 * dd.x);          // i * s3 * (b - c)
+            sm.fb[3 * j] = cadd(a, bc);
+            sm.fb[3 * j + 1] = cadd(mid, rot);                             // a + b w + c w^2, w = exp(+2 pi i / 3)
+            sm.fb[3 * j + 2] = csub(mid, rot);
+        }
+        __syncthreads();
+        if (tid < N / 8) pass8x<3>(sm.fb, sm.fa, sm.tw, tid);
+        __syncthreads();
+        if (tid < N / 8) pass8x<24>(sm.fa, sm.fb, sm.tw, tid);
+        __syncthreads();
+        if (tid < N / 8) {
+            // last pass (NS = 192) in registers: thread j ends up with channels k = j + 192 r, the same at every time
+            const int j = tid;
+            float2 v[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) v[r] = sm.fb[j + r * (N / 8)];
+#pragma unroll
+            for (int r = 1; r < 8; r++) v[r] = cmul(v[r], twid(sm.tw, r * j));
+            dft8(v);
+            if (t >= t_first) {
+                float* drow = dcap + (size_t)t * N;
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const float2 cur = v[r], prv = cprev[r];
+                    const float re = cur.x * prv.x + cur.y * prv.y;
+                    const float im = cur.y * prv.x - cur.x * prv.y;
+                    drow[j + r * (N / 8)] = atan2_branchfree(im, re) * P25_FM_GAIN;
+                    pw[r] += cur.x * cur.x + cur.y * cur.y;
+                }
+                if (p.y) {
+                    float2* yrow = p.y + ((size_t)cap * p.y_rows + t) * N;
+#pragma unroll
+                    for (int r = 0; r < 8; r++) yrow[j + r * (N / 8)] = v[r];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) cprev[r] = v[r];
+        }
+    }
+    if (p.power_sum && tid < N / 8) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) atomicAdd(p.power_sum + (size_t)cap * N + tid + r * (N / 8), pw[r]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel B
+// Boxcar over ten discriminator samples (oldest first, like the oracle) and transpose: a CTA takes 32 channels x 128
+// output times of d (128-byte row segments), every warp then writes 32 consecutive times of one channel's baseband row.
+constexpr int KC = 32;                 // channels per CTA
+constexpr int TB = 128;                // output times per CTA
+
+struct SmemB {
+    float dt[TB + DHIST][KC + 1];
+};
+
+struct ChanParams {
+    const float* d;            // [captures][d_rows][N]; row DHIST + t = output time t of this chunk, rows 0 .. DHIST-1 carried
+    float* bb;                 // baseband rows, stream = capture * N + channel
+    size_t row_stride;
+    unsigned n_out, n_captures, d_rows;
+};
+
+__global__ void __launch_bounds__(256) p25_chan_box_kernel(const ChanParams p) {
+    __shared__ SmemB sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned cap = blockIdx.z, k0 = blockIdx.y * KC;
-    const int t0 = blockIdx.x * TB;                               // first output time of the tile, relative to m0
-    const float2* yc = p.y + (size_t)cap * p.y_rows * N;
-    // rows of Y: row hist + t holds output time t of this chunk; rows [0, hist) are the previous chunk's last ones
-    for (int i = warp; i < TB + HALO; i += 8) {
-        const int t = t0 - HALO + i;
-        float2 v = make_float2(0.f, 0.f);
-        if (t < (int)p.n_out) v = __ldg(yc + (size_t)((int)p.hist + t) * N + k0 + lane);
-        sm.yt[i][lane] = v;
-    }
-    if (tid < KC) sm.pw[tid] = 0.f;
-    __syncthreads();
-    // channel-select FIR down each lane's column: c at time t0 - 10 + tc uses yt rows tc .. tc + 40
-    for (int blk = warp; blk * RC < TB + 10; blk += 8) {
-        const int tc0 = blk * RC;
-        float2 acc[RC];
-#pragma unroll
-        for (int r = 0; r < RC; r++) acc[r] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < HC + RC; i++) {
-            const int row = tc0 + i;
-            const float2 x = row < TB + HALO ? sm.yt[row][lane] : make_float2(0.f, 0.f);
-#pragma unroll
-            for (int r = 0; r < RC; r++) {
-                const int k = HC - i + r;
-                if (k >= 0 && k <= HC) acc[r] = cfma(c_chan[k], x, acc[r]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < RC; r++) sm.ct[tc0 + r][lane] = acc[r];
+    const int t0 = blockIdx.x * TB;
+    const float* dc = p.d + (size_t)cap * p.d_rows * N;
+    for (int i = warp; i < TB + DHIST; i += 8) {
+        const int t = t0 - DHIST + i;                              // row DHIST + t
+        sm.dt[i][lane] = t < (int)p.n_out ? __ldg(dc + (size_t)(DHIST + t) * N + k0 + lane) : 0.f;
     }
     __syncthreads();
-    // discriminator: d at time t0 - 9 + td from c rows td + 1, td; power of the stored outputs' c
-    float pw = 0.f;
-    for (int td = warp; td < TB + 9; td += 8) {
-        const float2 prv = sm.ct[td][lane], cur = sm.ct[td + 1][lane];
-        const float re = cur.x * prv.x + cur.y * prv.y;
-        const float im = cur.y * prv.x - cur.x * prv.y;
-        sm.dt[td][lane] = atan2_branchfree(im, re) * P25_FM_GAIN;
-        const int t = t0 - 9 + td;
-        if (t >= t0 && t < (int)p.n_out) pw += cur.x * cur.x + cur.y * cur.y;
-    }
-    if (p.power_sum) atomicAdd(&sm.pw[lane], pw);
-    __syncthreads();
-    // boxcar + transpose: a warp writes 32 consecutive output times of one channel
     for (int ch = warp; ch < KC; ch += 8) {
         float* out = p.bb + ((size_t)cap * N + k0 + ch) * p.row_stride + P25CU_BB_HIST;
         for (int o = lane; o < TB; o += 32) {
@@ -274,31 +306,38 @@ __global__ void __launch_bounds__(256) p25_chan_fm_kernel(const ChanParams p) {
             out[t] = acc * (1.0f / P25_BOXCAR);
         }
     }
-    if (p.power_sum && tid < KC) atomicAdd(p.power_sum + (size_t)cap * N + k0 + tid, sm.pw[tid]);
 }
 
-// carried input tail: tail_out[i] = logical[n + i], logical = tail_in ++ chunk (both cf32), i < L
+// carried input tail: tail_out[i] = logical[n + i], logical = tail_in ++ chunk (both cf32), i < HTX
 __global__ void p25_pfb_tail_kernel(const float2* iq, const float2* tail_in, float2* tail_out, unsigned n) {
     const unsigned cap = blockIdx.y;
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (unsigned)L) return;
+    if (i >= (unsigned)HTX) return;
     const unsigned long long l = (unsigned long long)n + i;
-    tail_out[(size_t)cap * L + i] = l < (unsigned long long)L ? tail_in[(size_t)cap * L + l] : iq[(size_t)cap * n + (l - L)];
+    tail_out[(size_t)cap * HTX + i] = l < (unsigned long long)HTX ? tail_in[(size_t)cap * HTX + l] : iq[(size_t)cap * n + (l - HTX)];
 }
 
 }  // namespace pfb
 
 // ------------------------------------------------------------------------------------------------ host side
-unsigned p25cu_pfb_tail_len() { return (unsigned)pfb::L; }
+unsigned p25cu_pfb_tail_len() { return (unsigned)pfb::HTX; }
 unsigned p25cu_pfb_channels() { return (unsigned)pfb::N; }
 unsigned p25cu_pfb_decimation() { return (unsigned)pfb::M; }
-unsigned p25cu_pfb_hist_rows() { return 64; }
+unsigned p25cu_pfb_hist_rows() { return (unsigned)pfb::DHIST; }
 
+// Equivalent prototype heq = hp (*) upsample(hc, M), in double, rounded once to f32; twiddle table.
 cudaError_t p25cu_pfb_upload(float** d_taps, float2** d_twiddle) {
     cudaError_t e;
-    if ((e = cudaMemcpyToSymbol(pfb::c_chan, P25_TAPS_CHAN_H, sizeof(float) * P25_TAPS_CHAN)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(d_taps, sizeof(float) * pfb::L)) != cudaSuccess) return e;
-    if ((e = cudaMemcpy(*d_taps, P25_TAPS_PFB_H, sizeof(float) * pfb::L, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    double* acc = new double[pfb::LE]();
+    for (int j = 0; j < P25_TAPS_CHAN; j++)
+        for (int i = 0; i < pfb::L; i++) acc[i + pfb::M * j] += (double)P25_TAPS_CHAN_H[j] * (double)P25_TAPS_PFB_H[i];
+    float* heq = new float[pfb::LE];
+    for (int i = 0; i < pfb::LE; i++) heq[i] = (float)acc[i];
+    delete[] acc;
+    if ((e = cudaMalloc(d_taps, sizeof(float) * pfb::LE)) == cudaSuccess)
+        e = cudaMemcpy(*d_taps, heq, sizeof(float) * pfb::LE, cudaMemcpyHostToDevice);
+    delete[] heq;
+    if (e != cudaSuccess) return e;
     float2* tw = new float2[pfb::N];
     for (int t = 0; t < pfb::N; t++) {
         const double a = 2.0 * 3.14159265358979323846 * (double)t / (double)pfb::N;
@@ -312,60 +351,54 @@ cudaError_t p25cu_pfb_upload(float** d_taps, float2** d_twiddle) {
 
 // Per-device setup (once per device under the library's plan mutex, that device current).
 cudaError_t p25cu_pfb_plan_device(P25DevPlan* plan) {
-    cudaError_t e = cudaFuncSetAttribute(pfb::p25_pfb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pfb::SmemA));
+    cudaError_t e = cudaFuncSetAttribute(pfb::p25_pfbx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pfb::SmemX));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(pfb::p25_chan_fm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pfb::SmemB));
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pfb::p25_pfb_kernel, pfb::NT, sizeof(pfb::SmemA));
-    if (e != cudaSuccess) return e;
-    plan->pfb_slots = plan->n_sm * (per_sm > 0 ? per_sm : 1);
+    plan->pfb_slots = plan->n_sm;          // one 222 KB CTA per SM
     return cudaSuccess;
 }
 
-// One chunk of every capture: spectrum rows into y (rows hist ..), baseband rows into bb, new tail.
-cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out, const float* taps, const float2* twiddle, float2* y,
-                             unsigned y_rows, float* bb, size_t row_stride, float* power_sum, unsigned long long a0,
-                             unsigned long long m0, unsigned n, unsigned n_out, unsigned n_captures, cudaStream_t st,
-                             unsigned* launches, const P25DevPlan* plan) {
-    const unsigned hist = p25cu_pfb_hist_rows();
+// One chunk of every capture: discriminator rows into d (rows DHIST ..), baseband rows into bb, new tail.
+cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out, const float* taps, const float2* twiddle, float* d,
+                             unsigned d_rows, float2* y, unsigned y_rows, float* bb, size_t row_stride, float* power_sum,
+                             unsigned long long a0, unsigned long long m0, unsigned n, unsigned n_out, unsigned n_captures,
+                             cudaStream_t st, unsigned* launches, const P25DevPlan* plan) {
     if (n_out) {
         pfb::PfbParams a;
         a.iq = (const float2*)iq;
         a.tail_in = (const float2*)tail_in;
         a.taps = taps;
         a.twiddle = twiddle;
+        a.d = d;
         a.y = y;
+        a.power_sum = power_sum;
         a.a0 = a0;
         a.m0 = m0;
         a.n = n;
         a.n_out = n_out;
         a.n_captures = n_captures;
+        a.d_rows = d_rows;
         a.y_rows = y_rows;
-        a.hist = hist;
-        // one wave of CTAs: consecutive output times per CTA (their windows overlap, so re-reads hit L1), as many CTAs
-        // as fit at once
-        const int slots = plan->pfb_slots;
-        unsigned per_cap = (unsigned)slots / n_captures;
+        // one wave: every SM gets one run of consecutive output times (each run pays one window fill and one warm-up
+        // output time), the captures share the SMs evenly
+        unsigned per_cap = (unsigned)plan->pfb_slots / n_captures;
         if (per_cap < 1) per_cap = 1;
-        const unsigned tpc = (n_out + per_cap - 1) / per_cap;            // output times per CTA
+        unsigned tpc = (n_out + per_cap - 1) / per_cap;                  // output times per CTA
+        if (tpc < 8) tpc = n_out < 8 ? n_out : 8;
         const dim3 ga((n_out + tpc - 1) / tpc, n_captures);
-        pfb::p25_pfb_kernel<<<ga, pfb::NT, sizeof(pfb::SmemA), st>>>(a, tpc);
+        pfb::p25_pfbx_kernel<<<ga, pfb::NTX, sizeof(pfb::SmemX), st>>>(a, tpc);
         pfb::ChanParams b;
-        b.y = y;
+        b.d = d;
         b.bb = bb;
         b.row_stride = row_stride;
-        b.power_sum = power_sum;
         b.n_out = n_out;
         b.n_captures = n_captures;
-        b.y_rows = y_rows;
-        b.hist = hist;
+        b.d_rows = d_rows;
         const dim3 gb((n_out + pfb::TB - 1) / pfb::TB, pfb::N / pfb::KC, n_captures);
-        pfb::p25_chan_fm_kernel<<<gb, 256, sizeof(pfb::SmemB), st>>>(b);
+        pfb::p25_chan_box_kernel<<<gb, 256, 0, st>>>(b);
         *launches += 2;
     }
     if (n) {
-        const dim3 gt((pfb::L + 255) / 256, n_captures);
+        const dim3 gt((pfb::HTX + 255) / 256, n_captures);
         pfb::p25_pfb_tail_kernel<<<gt, 256, 0, st>>>((const float2*)iq, (const float2*)tail_in, (float2*)tail_out, n);
         *launches += 1;
     }

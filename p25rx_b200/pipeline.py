@@ -178,8 +178,13 @@ class Context:
         self._ck(self._L.p25cu_read_baseband(self._h, stream, out.ctypes.data_as(C.c_void_p), n))
         return out
 
+    def keep_spectra(self, on: bool = True):
+        """Channelizer mode test hook: keep the channel-filtered spectra of every following demod for channelizer_output()."""
+        self._ck(self._L.p25cu_set_keep_spectra(self._h, int(on)))
+
     def channelizer_output(self) -> np.ndarray:
-        """Channelizer mode (decimation 400): channel spectra of the last demod, [captures][n_out][1536] complex64."""
+        """Channelizer mode (decimation 400): channel spectra (after the channel-select filter) of the last demod,
+        [captures][n_out][1536] complex64; needs keep_spectra() before that demod."""
         n = C.c_size_t(0)
         self._ck(self._L.p25cu_channelizer_output(self._h, None, C.byref(n)))
         out = np.zeros((self.n_streams // 1536, n.value, 1536), dtype=np.complex64)

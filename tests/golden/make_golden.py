@@ -38,11 +38,12 @@ def main():
     np.savez_compressed(os.path.join(os.path.dirname(__file__), "demod_golden.npz"), iq_u8=iq,
                         baseband=np.concatenate([p[0] for p in parts]), power_dbm=np.array([p[1] for p in parts], dtype=np.float32))
 
-    # channelizer fixture: 19.2 MS/s capture -> channel spectra (oracle/pfb_oracle.py), the last 8 output times of 96 channels
+    # channelizer fixture: 19.2 MS/s capture -> channel spectra after the channel-select filter (oracle/pfb_oracle.py:
+    # channel_filter(channelize(x)), what the kernels deliver), the last 8 output times of 96 channels
     from oracle import pfb_oracle as pfb
     st = tx.control_channel(951, 1, lead_idle=0)
     cap = tx.wideband_capture({5: (st.dibits, 0.05, 0.0), 1530: (st.dibits[::-1].copy(), 0.03, 50.0)}, 12_000, noise_db=-50.0, seed=9)
-    y = pfb.channelize(cap)
+    y = pfb.channel_filter(pfb.channelize(cap))
     np.savez_compressed(os.path.join(os.path.dirname(__file__), "pfb_golden.npz"), capture=cap, rows=np.arange(22, 30),
                         channels=np.arange(0, 1536, 16) + 5 % 16, spectra=y[22:30][:, (np.arange(0, 1536, 16) + 5 % 16)].astype(np.complex64))
     print("demod", sum(len(p[0]) for p in parts), "baseband samples; pfb", y.shape)

@@ -32,6 +32,18 @@ def test_offset_start_matches_whole_stream():
     assert np.allclose(whole[33:53], part, rtol=0, atol=1e-12)
 
 
+def test_channel_filter_folds_into_the_prototype():
+    """The identity the round-2 kernels rest on: the reference's 41-tap channel filter down every channel column equals
+    ONE polyphase pass with the equivalent prototype hp (*) upsample(hc, 400) (15 taps per branch instead of 4)."""
+    rng = np.random.default_rng(8)
+    x = (rng.standard_normal(400 * 70) + 1j * rng.standard_normal(400 * 70)).astype(np.complex64)
+    two_step = po.channel_filter(po.channelize(x))
+    fused = po.channelize_fused(x)
+    assert np.max(np.abs(two_step - fused)) < 1e-6 * np.max(np.abs(two_step))        # f32 rounding of the fused taps only
+    heq = po.equivalent_prototype()
+    assert len(heq) == 6144 + 400 * 40 and abs(heq.sum() - 1.0) < 1e-6 and -(-len(heq) // 1536) == 15
+
+
 def test_prototype_filter_meets_its_spec():
     h = S.taps_pfb().astype(np.float64)
     assert len(h) == S.PFB_TAPS_LEN == 6144 and abs(h.sum() - 1.0) < 1e-6

@@ -7,7 +7,7 @@ the polyphase filter bank, every channel demodulated and decoded.
 
 One step = one chunk of every capture through p25cu_process + p25cu_poll.  Prints one JSON line with per-kernel
 times (CUDA events around the serialised kernels), the real-time factor and the HBM roofline of the two kernels
-(algorithmic bytes per input sample: 8 in + 30.72 spectra out | 30.72 spectra in + 15.36 baseband out)."""
+(algorithmic bytes per input sample: 8 in + 15.36 baseband out)."""
 from __future__ import annotations
 
 import argparse
@@ -88,7 +88,7 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         peak = 6650.0
-    alg = args.captures * n * (8 + 2 * 30.72 + 15.36)
+    alg = args.captures * n * (8 + 15.36)          # SURVEY 8d style: 8 B per input sample in, 4 B per channel and output time out
     line = {"shape": {"captures": args.captures, "sample_rate": fs, "chunk_ms": args.chunk_ms, "channels": S, "occupied": args.occupied,
                       "input_mb_per_step": args.captures * n * 8 / 1e6},
             "step_ms": step_ms, "channelizer_plus_baseband_ms_serial": demod_ms, "walk_ms_serial": walk_ms,
