@@ -77,4 +77,13 @@ extern "C" {
     pub fn p25cu_sync(ctx: *mut p25cu_ctx) -> c_int;
     pub fn p25cu_set_overlap(ctx: *mut p25cu_ctx, on: c_int) -> c_int;
     pub fn p25cu_channelizer_output(ctx: *mut p25cu_ctx, out: *mut f32, n_rows: *mut size_t) -> c_int;
+    // round 2 (include/p25cu.h): packed asynchronous drain, pinned chunk buffers
+    pub fn p25cu_poll_start(ctx: *mut p25cu_ctx) -> i32;
+    pub fn p25cu_poll_packed(ctx: *mut p25cu_ctx, words: *mut *const u32, n_words: *mut usize, n_events: *mut usize,
+                             more: *mut i32) -> i32;
+    pub fn p25cu_unpack_events(words: *const u32, n_words: usize, out: *mut p25cu_event, cap: usize, n: *mut usize) -> i32;
+    pub fn p25cu_host_alloc(ctx: *mut p25cu_ctx, bytes: usize, out: *mut *mut std::ffi::c_void) -> i32;
+    pub fn p25cu_host_free(ctx: *mut p25cu_ctx, p: *mut std::ffi::c_void) -> i32;
+    pub fn p25cu_host_register(ctx: *mut p25cu_ctx, p: *mut std::ffi::c_void, bytes: usize) -> i32;
+    pub fn p25cu_host_unregister(ctx: *mut p25cu_ctx, p: *mut std::ffi::c_void) -> i32;
 }

@@ -117,7 +117,10 @@ static_assert(HTX >= LE + M - 1 && RING >= LE + 2 * M, "window + prefetch must f
 struct SmemX {
     float2 ring[RING];
     float2 fa[N], fb[N];
-    float2 tw[N / 2];                  // exp(+2 pi i t / N), t < N / 2; the other half is its negative
+    // first twiddle of every radix-8 butterfly, laid out by the lane index of its pass (conflict-free LDS.64); the
+    // other six are its powers, formed in registers (a 1,536-entry table indexed r * k * stride put up to 32 lanes
+    // on one bank: 26 % of the kernel's shared-memory wavefronts in the first version)
+    float2 tw3[4], tw24[24], tw192[N / 8];   // exp(+2 pi i k / 24), exp(+2 pi i k / 192), exp(+2 pi i k / 1536)
 };
 
 struct PfbParams {
@@ -138,24 +141,66 @@ __device__ __forceinline__ float2 load_logical(const PfbParams& p, const float2*
     const long long i = l - HTX;
     return i < (long long)p.n ? __ldg(chunk + i) : make_float2(0.f, 0.f);
 }
-__device__ __forceinline__ float2 twid(const float2* tw, int t) {   // t in [0, N)
-    const float2 w = tw[t < N / 2 ? t : t - N / 2];
-    return t < N / 2 ? w : make_float2(-w.x, -w.y);
+// w^1 .. w^7 from w: six complex multiplies, depth three
+__device__ __forceinline__ void powers7(float2 w1, float2 (&w)[8]) {
+    w[1] = w1;
+    w[2] = cmul(w1, w1);
+    w[3] = cmul(w[2], w1);
+    w[4] = cmul(w[2], w[2]);
+    w[5] = cmul(w[4], w1);
+    w[6] = cmul(w[3], w[3]);
+    w[7] = cmul(w[6], w1);
 }
 
-// one radix-8 Stockham pass with the half twiddle table
+// one radix-8 Stockham pass; w1 = exp(+2 pi i (j % NS) / (8 NS)) is the butterfly's first twiddle
 template <int NS>
-__device__ __forceinline__ void pass8x(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ tw, int j) {
-    const int k = j % NS;
-    float2 v[8];
+__device__ __forceinline__ void pass8x(const float2* __restrict__ in, float2* __restrict__ out, float2 w1, int j) {
+    float2 v[8], w[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) v[r] = in[j + r * (N / 8)];
+    powers7(w1, w);
 #pragma unroll
-    for (int r = 1; r < 8; r++) v[r] = cmul(v[r], twid(tw, r * k * (N / (NS * 8))));
+    for (int r = 1; r < 8; r++) v[r] = cmul(v[r], w[r]);
     dft8(v);
-    const int j0 = (j / NS) * NS * 8 + k;
+    const int j0 = (j / NS) * NS * 8 + (j % NS);
 #pragma unroll
     for (int r = 0; r < 8; r++) out[j0 + r * NS] = v[r];
+}
+
+// branch sum of one polyphase branch whose window starts in ring row R0 (mod 16): every row offset is a constant
+template <int R0>
+__device__ __forceinline__ float2 branch_sum(const float2* __restrict__ col, const float (&tap)[PE]) {
+    float2 x[PE];
+#pragma unroll
+    for (int pp = 0; pp < PE; pp++) x[pp] = col[((R0 - pp) & (RROWS - 1)) * N];        // all 15 loads in flight first
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;                               // three chains of five: 20 instead of 60 cycles deep
+#pragma unroll
+    for (int pp = 0; pp < PE; pp += 3) {
+        a0 = cfma(tap[pp], x[pp], a0);
+        a1 = cfma(tap[pp + 1], x[pp + 1], a1);
+        a2 = cfma(tap[pp + 2], x[pp + 2], a2);
+    }
+    return cadd(cadd(a0, a1), a2);
+}
+__device__ __forceinline__ float2 branch_sum_dyn(unsigned row0, const float2* __restrict__ col, const float (&tap)[PE]) {
+    switch (row0 & (RROWS - 1)) {       // warp-uniform up to the one column where the window wraps
+        case 0: return branch_sum<0>(col, tap);
+        case 1: return branch_sum<1>(col, tap);
+        case 2: return branch_sum<2>(col, tap);
+        case 3: return branch_sum<3>(col, tap);
+        case 4: return branch_sum<4>(col, tap);
+        case 5: return branch_sum<5>(col, tap);
+        case 6: return branch_sum<6>(col, tap);
+        case 7: return branch_sum<7>(col, tap);
+        case 8: return branch_sum<8>(col, tap);
+        case 9: return branch_sum<9>(col, tap);
+        case 10: return branch_sum<10>(col, tap);
+        case 11: return branch_sum<11>(col, tap);
+        case 12: return branch_sum<12>(col, tap);
+        case 13: return branch_sum<13>(col, tap);
+        case 14: return branch_sum<14>(col, tap);
+        default: return branch_sum<15>(col, tap);
+    }
 }
 
 __global__ void __launch_bounds__(NTX, 1) p25_pfbx_kernel(const PfbParams p, const unsigned times_per_cta) {
@@ -168,7 +213,9 @@ __global__ void __launch_bounds__(NTX, 1) p25_pfbx_kernel(const PfbParams p, con
     if (t_first >= t_last) return;
     const float2* chunk = p.iq + (size_t)cap * p.n;
     const float2* tail = p.tail_in + (size_t)cap * HTX;
-    for (int i = tid; i < N / 2; i += NTX) sm.tw[i] = p.twiddle[i];
+    if (tid < N / 8) sm.tw192[tid] = p.twiddle[tid];
+    if (tid < 24) sm.tw24[tid] = p.twiddle[8 * tid];
+    if (tid < 3) sm.tw3[tid] = p.twiddle[64 * tid];
     float tap[3][PE];
 #pragma unroll
     for (int b = 0; b < 3; b++)
@@ -205,9 +252,7 @@ __global__ void __launch_bounds__(NTX, 1) p25_pfbx_kernel(const PfbParams p, con
             const int r = tid + NTX * b;
             const unsigned J = (unsigned)(e - r);
             const unsigned row0 = J / N, col = J - row0 * N;
-            float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int pp = 0; pp < PE; pp++) acc = cfma(tap[b][pp], sm.ring[((row0 - pp) & (RROWS - 1)) * N + col], acc);
+            const float2 acc = branch_sum_dyn(row0, sm.ring + col, tap[b]);
             int q = r - nm_mod;
             if (q < 0) q += N;
             sm.fa[q] = acc;
@@ -228,18 +273,19 @@ __global__ void __launch_bounds__(NTX, 1) p25_pfbx_kernel(const PfbParams p, con
             sm.fb[3 * j + 2] = csub(mid, rot);
         }
         __syncthreads();
-        if (tid < N / 8) pass8x<3>(sm.fb, sm.fa, sm.tw, tid);
+        if (tid < N / 8) pass8x<3>(sm.fb, sm.fa, sm.tw3[tid % 3], tid);
         __syncthreads();
-        if (tid < N / 8) pass8x<24>(sm.fa, sm.fb, sm.tw, tid);
+        if (tid < N / 8) pass8x<24>(sm.fa, sm.fb, sm.tw24[tid % 24], tid);
         __syncthreads();
         if (tid < N / 8) {
             // last pass (NS = 192) in registers: thread j ends up with channels k = j + 192 r, the same at every time
             const int j = tid;
-            float2 v[8];
+            float2 v[8], w[8];
 #pragma unroll
             for (int r = 0; r < 8; r++) v[r] = sm.fb[j + r * (N / 8)];
+            powers7(sm.tw192[j], w);
 #pragma unroll
-            for (int r = 1; r < 8; r++) v[r] = cmul(v[r], twid(sm.tw, r * j));
+            for (int r = 1; r < 8; r++) v[r] = cmul(v[r], w[r]);
             dft8(v);
             if (t >= t_first) {
                 float* drow = dcap + (size_t)t * N;
