@@ -20,10 +20,9 @@ cudaError_t p25cu_walk_upload_consts();
 unsigned p25cu_pfb_tail_len();
 unsigned p25cu_pfb_channels();
 unsigned p25cu_pfb_decimation();
-unsigned p25cu_pfb_hist_rows();
 cudaError_t p25cu_pfb_upload(float** d_taps, float2** d_twiddle);
-cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out, const float* taps, const float2* twiddle, float* d,
-                             unsigned d_rows, float2* y, unsigned y_rows, float* bb, size_t row_stride, float* power_sum,
+cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out, const float* taps, const float2* twiddle,
+                             float2* y, unsigned y_rows, float* bb, size_t row_stride, float* power_sum,
                              unsigned long long a0, unsigned long long m0, unsigned n, unsigned n_out, unsigned n_captures,
                              cudaStream_t st, unsigned* launches, const P25DevPlan* plan);
 
@@ -87,9 +86,6 @@ struct p25cu_ctx {
     unsigned n_captures;       // 0 = one stream per input row
     float* d_pfb_taps;
     float2* d_twiddle;
-    float* d_d;                // [captures][d_rows][1536] discriminator output, time-major: 9 carried rows | this chunk
-    float* d_dtmp;             // [captures][9][1536] staging for the carried rows
-    unsigned d_rows;
     float2* d_y;               // [captures][y_rows][1536] channel-filtered spectra of the last chunk (test hook, lazy)
     unsigned y_rows;
     int keep_spectra;
@@ -138,8 +134,6 @@ extern "C" void p25cu_destroy(p25cu_ctx* ctx) {
     cudaFree(ctx->d_golay);
     cudaFree(ctx->d_pfb_taps);
     cudaFree(ctx->d_twiddle);
-    cudaFree(ctx->d_d);
-    cudaFree(ctx->d_dtmp);
     cudaFree(ctx->d_y);
     cudaFreeHost(ctx->h_events);
     for (int i = 0; i < 2; i++) {
@@ -220,12 +214,7 @@ static int create_impl(p25cu_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->d_tail[0], 0, tail_rows * ctx->ht * sizeof(float2), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_tail[1], 0, tail_rows * ctx->ht * sizeof(float2), ctx->stream));
     if (wide) {
-        const size_t ch = p25cu_pfb_channels(), hist = p25cu_pfb_hist_rows();
-        ctx->d_rows = (unsigned)(hist + ctx->max_out);
         ctx->y_rows = (unsigned)ctx->max_out;
-        CK(cudaMalloc(&ctx->d_d, (size_t)ctx->n_captures * ctx->d_rows * ch * sizeof(float)));
-        CK(cudaMemsetAsync(ctx->d_d, 0, (size_t)ctx->n_captures * ctx->d_rows * ch * sizeof(float), ctx->stream));
-        CK(cudaMalloc(&ctx->d_dtmp, (size_t)ctx->n_captures * hist * ch * sizeof(float)));
         CK(p25cu_pfb_upload(&ctx->d_pfb_taps, &ctx->d_twiddle));
     }
     for (int i = 0; i < 2; i++) {
@@ -364,20 +353,13 @@ extern "C" int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_d
     if (timed) CK(cudaEventRecord(ctx->tev[2 * ctx->n_timed], ctx->stream));
     if (n && ctx->n_captures) {
         // wideband capture -> 1,536 channels per capture (pfb.cu): discriminator rows, per-channel baseband, carried state
-        const size_t ch = p25cu_pfb_channels(), hist = p25cu_pfb_hist_rows();
+        const size_t ch = p25cu_pfb_channels();
         unsigned nl = 0;
         if (ctx->keep_spectra && !ctx->d_y) CK(cudaMalloc(&ctx->d_y, (size_t)ctx->n_captures * ctx->y_rows * ch * sizeof(float2)));
-        CK(p25cu_launch_pfb(d_in, p.tail_in, p.tail_out, ctx->d_pfb_taps, ctx->d_twiddle, ctx->d_d, ctx->d_rows,
-                            ctx->keep_spectra ? ctx->d_y : nullptr, ctx->y_rows, p.bb, p.row_stride, p.power_sum, p.a0, p.m0, p.n, p.n_out,
-                            ctx->n_captures, ctx->stream, &nl, ctx->plan));
+        CK(p25cu_launch_pfb(d_in, p.tail_in, p.tail_out, ctx->d_pfb_taps, ctx->d_twiddle, ctx->keep_spectra ? ctx->d_y : nullptr,
+                            ctx->y_rows, p.bb, p.row_stride, p.power_sum, p.a0, p.m0, p.n, p.n_out, ctx->n_captures, ctx->stream, &nl,
+                            ctx->plan));
         ctx->launches += nl;
-        if (p.n_out) {   // the last `hist` rows of (carried rows ++ this chunk) become the next chunk's carried rows
-            const size_t row = ch * sizeof(float);
-            CK(cudaMemcpy2DAsync(ctx->d_dtmp, hist * row, ctx->d_d + (size_t)p.n_out * ch, (size_t)ctx->d_rows * row, hist * row,
-                                 ctx->n_captures, cudaMemcpyDeviceToDevice, ctx->stream));
-            CK(cudaMemcpy2DAsync(ctx->d_d, (size_t)ctx->d_rows * row, ctx->d_dtmp, hist * row, hist * row, ctx->n_captures,
-                                 cudaMemcpyDeviceToDevice, ctx->stream));
-        }
         ctx->tail_cur ^= 1;
     } else if (n) {
         CK(p25cu_launch_ddc(p, ctx->cfg.format, ctx->cfg.decimation, ctx->stream));

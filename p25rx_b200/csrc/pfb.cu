@@ -16,21 +16,31 @@
 //   v_m[r] = sum_{p<4} h[r + 1536 p] x[n_m - r - 1536 p]           (4 complex-by-real taps per branch)
 //   y_k[m] = sum_q v_m[(q + n_m) mod 1536] exp(+2j pi k q / 1536)   (one 1,536-point inverse DFT per output time)
 //
-// Round 2 folds the channel-select FIR into the prototype (see kernel A below): kernel A = polyphase branches + FFT +
-// discriminator, kernel B = boxcar + transpose.  Algorithmic HBM traffic: 8 B per input sample in, 4 B per channel and
-// output time out (15.4 B per input sample); the discriminator rows between the two kernels add 2 x 15.4 B.
+// Round 2 folds the channel-select FIR into the prototype and does everything in ONE kernel (below): polyphase
+// branches, inverse DFT, discriminator, boxcar, baseband rows.  HBM traffic is the algorithmic minimum: 8 B per input
+// sample in, 4 B per channel and output time out (15.4 B per input sample).
+#include <cooperative_groups.h>
+
 #include "p25cu_internal.cuh"
 #include "p25_pfb_taps.h"
 
 namespace pfb {
 
 constexpr int N = P25_PFB_N, M = P25_PFB_M, P = P25_PFB_P, L = N * P;
-constexpr int NT = 256;
 static_assert(N == 3 * 8 * 8 * 8, "FFT plan is 3 x 8 x 8 x 8");
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract on the packed FP32 pipe: one FADD2 each
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
 __device__ __forceinline__ float2 mul_i(float2 a) { return make_float2(-a.y, a.x); }     // a * (+i)
 // acc += h * x on both components: one FFMA2
 __device__ __forceinline__ float2 cfma(float h, float2 x, float2 acc) {
@@ -86,41 +96,66 @@ __device__ __forceinline__ float atan2_branchfree(float y, float x) {   // same 
     return copysignf(r, y);
 }
 
-// ------------------------------------------------------------------------------------------------ kernel A
-// Round 2: the per-channel channel-select FIR (41 taps at 48 kS/s, src/demod.rs:93) is folded into the prototype.
-// Channel k after the channel filter is
+// ------------------------------------------------------------------------------------------------ the kernel
+// Round 2 folds the per-channel channel-select FIR (41 taps at 48 kS/s, src/demod.rs:93) into the prototype.  Channel k
+// after the channel filter is
 //     c_k[m] = sum_j hc[j] y_k[m - j] = sum_i heq[i] x[n_m - i] exp(-2j pi k (n_m - i) / N),
 //     heq = hp (*) upsample(hc, M)           (6,144 + 40 * 400 = 22,144 taps, zero-padded to PE * N = 23,040)
 // i.e. the same polyphase form with PE = 15 taps per branch instead of 4 -- 23,040 complex-by-real MACs per output time
-// for all 1,536 channels, instead of 6,144 + 1,536 * 41 = 69,120 -- and no [time][channel] spectra round trip through HBM
-// before the FIR (the round-1 design moved 61 bytes per input sample there).
+// for all 1,536 channels, instead of 6,144 + 1,536 * 41 = 69,120 -- and no [time][channel] round trip through HBM.
 //
-// A CTA (512 threads, one per SM: 222 KB of shared memory) owns a run of consecutive output times of one capture:
-//   * the input window lives in a shared-memory ring of 16 x 1,536 samples (192 KB) indexed by the logical sample
-//     index (carried tail ++ chunk); every output time brings M = 400 new samples, prefetched one step ahead;
-//   * a thread owns three polyphase branches r = tid + 512 b and keeps their 45 prototype taps in registers for the
-//     whole run, so the branch sums cost one LDS.64 + one FFMA2 per tap;
-//   * the 1,536-point inverse DFT is the mixed-radix Stockham FFT 3 x 8 x 8 x 8 in shared memory; its last pass leaves
-//     every thread with the same eight channels at every output time, so the previous c_k[m - 1] stays in registers and
-//     the FM discriminator (src/demod.rs:109-111) runs right there: only d_k[m] (4 bytes per channel and time) goes to
-//     HBM, time-major; power (src/demod.rs:95-101) accumulates in registers;
-//   * one warm-up output time per run supplies c_k[m0 - 1].
-// Kernel B then only applies the 10-tap boxcar (src/demod.rs:114) along time and transposes into the baseband rows.
+// Every one of those MACs pairs a distinct (sample, tap): nothing is reused, so one of the two has to come out of
+// shared memory for every FFMA2.  The first round-2 kernel kept the taps in registers and the 23,040-sample window in a
+// 192 KB ring (8 bytes per MAC, one CTA per SM, no room left to batch the FFT).  This one turns it round:
+//
+//   * CLASS-STATIONARY WINDOWS IN REGISTERS.  The samples that feed FFT input q are exactly those with index
+//     s = -q (mod N): a thread owns two such residue classes and keeps the newest 16 samples of each in registers as a
+//     circular window.  Per MAC only the 4-byte tap comes from shared memory: the 16 taps that go with a window whose
+//     newest sample lies d0 = n_m - s_newest inputs back are one table row, tap[k] = heq[d0 + N k] (zero outside
+//     0 .. LE - 1), read with four conflict-free LDS.128.  A class receives a new sample in 400 of every 1,536 output
+//     times; the 32 classes of a warp are consecutive samples and always advance TOGETHER, at the output time the first
+//     of them needs it -- the others then hold a sample up to 62 inputs "from the future" in their newest slot, which
+//     the row for their (negative) d0 multiplies by zero.  So the slot that is overwritten is warp-uniform and the
+//     branch sum is a jump over 16 compile-time rotations of the same 16 FFMA2.
+//   * A CLUSTER OF TWO CTAs PER RUN OF OUTPUT TIMES.  1,536 windows are 46 K registers -- too many beside an FFT on one
+//     SM.  CTA b of the pair owns the classes of parity b: 768 windows (23 K registers), only the tap rows of the
+//     opposite parity (n_m is odd: 89 KB instead of 178), and the 768-point inverse DFT over its own inputs
+//     (q = 2u + b).  The last radix-2 step   c_k' = E[k'] + w^k' O[k'],  c_k'+768 = E[k'] - w^k' O[k']   reads the
+//     partner's half through distributed shared memory; CTA b finishes the channels k' in [384 b, 384 b + 384) and
+//     k' + 768.
+//   * EIGHT OUTPUT TIMES PER PASS.  The 768-point transforms of eight consecutive output times go through the three
+//     Stockham passes 8 x 8 x 12 together (96 / 96 / 64 butterflies per time: 768 / 768 / 512 per batch for 384
+//     threads), five CTA barriers and one cluster barrier per eight output times instead of six per time.
+//   * EVERYTHING AFTER THE FFT IS THREAD-LOCAL.  The combine step leaves thread k' with the same two channels at every
+//     output time: c[m-1] for the FM discriminator (src/demod.rs:109-111), the nine older discriminator values of the
+//     10-tap boxcar (src/demod.rs:114) and the power sum (src/demod.rs:95-101) stay in its registers, and it writes
+//     eight consecutive baseband samples of each channel (32 bytes) straight into the walker's rows.
+//   * A run starts with 10 warm-up output times (c[m-1] and nine discriminator values), recomputed from the carried
+//     input tail instead of carrying discriminator rows between chunks.
+// The index arithmetic is restated thread for thread in spec/pfb_dataflow.py and checked against the float64 oracle on
+// the CPU (tests/test_pfb_oracle.py).
 constexpr int PE = 15;                 // taps per branch of the equivalent prototype
 constexpr int LE = N * PE;             // 23,040
-constexpr int HTX = 23552;             // carried input tail (>= LE + M - 1, a multiple of 128)
-constexpr int RROWS = 16, RING = RROWS * N;
-constexpr int NTX = 512;
-constexpr int DHIST = P25_BOXCAR - 1;  // discriminator rows carried in front of every chunk (9)
-static_assert(HTX >= LE + M - 1 && RING >= LE + 2 * M, "window + prefetch must fit");
+constexpr int H = N / 2;               // FFT length per parity / CTA
+constexpr int NTH = 384;               // threads per CTA: two classes each
+constexpr int TB = 8;                  // output times per batch
+constexpr int WARM = 10;               // warm-up output times of a run
+constexpr int WS = 16;                 // window slots per class: 15 taps + one sample that may be early
+constexpr int HTX = 27648;             // carried input tail (>= LE + (WARM + 1) * M + 64, a multiple of 128)
+constexpr int EARLY = 64;              // a window's newest sample lies at most this far ahead of n_m (a warp spans 62)
+constexpr int ROWS = (N + EARLY) / 2;  // tap rows per CTA: d0 = 2 row - EARLY + (1 - b), d0 in [-EARLY, N)
+constexpr int FSK = H + H / 8;         // a time's FFT buffer with one pad element per eight (see skew())
+static_assert(HTX >= LE + (WARM + 1) * M + EARLY && HTX % 128 == 0, "warm-up windows must lie inside the carried tail");
+static_assert(M < N && N - M - 62 > 0, "a class receives at most one new sample per output time");
 
-struct SmemX {
-    float2 ring[RING];
-    float2 fa[N], fb[N];
-    // first twiddle of every radix-8 butterfly, laid out by the lane index of its pass (conflict-free LDS.64); the
-    // other six are its powers, formed in registers (a 1,536-entry table indexed r * k * stride put up to 32 lanes
-    // on one bank: 26 % of the kernel's shared-memory wavefronts in the first version)
-    float2 tw3[4], tw24[24], tw192[N / 8];   // exp(+2 pi i k / 24), exp(+2 pi i k / 192), exp(+2 pi i k / 1536)
+struct SmemC {
+    float4 tab[4][ROWS];               // tab[g][row] = taps 4 g .. 4 g + 3 of the row: tap[k] = heq[d0 + N k] or 0
+    float2 f0[TB][FSK];                // polyphase sums -> passes A and B in place
+    float2 own[TB][H / 2];             // this CTA's transform at the 384 k' it combines itself
+    float2 inc[2][TB][H / 2];          // the partner's transform at the same k', written by the partner (st.async), two batches deep
+    unsigned long long mbar[2];        // one transaction barrier per incoming buffer
+    float2 twB[64];                    // exp(+2 pi i k r / 64) at [8 k + r]
+    float2 twC[12][64];                // exp(+2 pi i j r / 768) at [r][j]
 };
 
 struct PfbParams {
@@ -128,231 +163,371 @@ struct PfbParams {
     const float2* tail_in;     // [captures][HTX]
     const float* taps;         // [LE] equivalent prototype (prototype (*) upsampled channel filter)
     const float2* twiddle;     // [N] exp(+2 pi i t / N)
-    float* d;                  // [captures][d_rows][N] discriminator output, time-major; this chunk's rows start at DHIST
+    float* bb;                 // baseband rows, stream = capture * N + channel
+    size_t row_stride;
     float2* y;                 // nullable: [captures][y_rows][N] channel-filtered spectra c_k[m] of this chunk (test hook)
     float* power_sum;          // nullable: [captures * N]
     unsigned long long a0, m0; // absolute input / output index of the chunk start
     unsigned n, n_out, n_captures;
-    unsigned d_rows, y_rows;
+    unsigned y_rows;
+    unsigned runs_per_cap, times_per_run;      // times_per_run is a multiple of TB
 };
 
-__device__ __forceinline__ float2 load_logical(const PfbParams& p, const float2* tail, const float2* chunk, long long l) {
-    if (l < HTX) return l >= 0 ? tail[l] : make_float2(0.f, 0.f);
-    const long long i = l - HTX;
-    return i < (long long)p.n ? __ldg(chunk + i) : make_float2(0.f, 0.f);
+// sample at logical index l of (carried tail ++ chunk); zeros outside
+__device__ __forceinline__ float2 load_logical(const float2* __restrict__ tail, const float2* __restrict__ chunk, int n, int l) {
+    const bool in_chunk = l >= HTX;
+    const float2* ptr = in_chunk ? chunk + (l - HTX) : tail + l;
+    return (l >= 0 && l < HTX + n) ? __ldg(ptr) : make_float2(0.f, 0.f);
 }
-// w^1 .. w^7 from w: six complex multiplies, depth three
-__device__ __forceinline__ void powers7(float2 w1, float2 (&w)[8]) {
-    w[1] = w1;
-    w[2] = cmul(w1, w1);
-    w[3] = cmul(w[2], w1);
-    w[4] = cmul(w[2], w[2]);
-    w[5] = cmul(w[4], w1);
-    w[6] = cmul(w[3], w[3]);
-    w[7] = cmul(w[6], w1);
+__device__ __forceinline__ int skew(int i) { return i + (i >> 3); }
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// the partner CTA's copy of a shared-memory address of this CTA
+__device__ __forceinline__ unsigned map_to_rank(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// 8-byte store into the partner's shared memory that counts its bytes on the partner's transaction barrier: the data
+// path needs no cluster-wide barrier and no fence (a release at cluster scope compiles to MEMBAR.ALL.GPU, an acquire to
+// CCTL.IVALL: 18 % of all warp stalls in the first version of this kernel)
+__device__ __forceinline__ void st_async_f2(unsigned remote_addr, float2 v, unsigned remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+                 :: "r"(remote_addr), "f"(v.x), "f"(v.y), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "P25_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra P25_MBAR_DONE;\n"
+        "bra P25_MBAR_WAIT;\n"
+        "P25_MBAR_DONE:\n"
+        "}\n" :: "r"(mbar), "r"(parity) : "memory");
 }
 
-// one radix-8 Stockham pass; w1 = exp(+2 pi i (j % NS) / (8 NS)) is the butterfly's first twiddle
-template <int NS>
-__device__ __forceinline__ void pass8x(const float2* __restrict__ in, float2* __restrict__ out, float2 w1, int j) {
-    float2 v[8], w[8];
+// 12-point DFT with the + sign, r = 3 a + b, q = q1 + 4 q2: three 4-point DFTs over a, twiddles W12^(b q1), four
+// 3-point DFTs over b.  In place: v[q].
+__device__ __forceinline__ void dft12(float2 (&v)[12]) {
+    const float c6 = 0.86602540378443865f;          // cos(pi / 6) = sin(pi / 3)
+    float2 z[3][4];
 #pragma unroll
-    for (int r = 0; r < 8; r++) v[r] = in[j + r * (N / 8)];
-    powers7(w1, w);
-#pragma unroll
-    for (int r = 1; r < 8; r++) v[r] = cmul(v[r], w[r]);
-    dft8(v);
-    const int j0 = (j / NS) * NS * 8 + (j % NS);
-#pragma unroll
-    for (int r = 0; r < 8; r++) out[j0 + r * NS] = v[r];
-}
-
-// branch sum of one polyphase branch whose window starts in ring row R0 (mod 16): every row offset is a constant
-template <int R0>
-__device__ __forceinline__ float2 branch_sum(const float2* __restrict__ col, const float (&tap)[PE]) {
-    float2 x[PE];
-#pragma unroll
-    for (int pp = 0; pp < PE; pp++) x[pp] = col[((R0 - pp) & (RROWS - 1)) * N];        // all 15 loads in flight first
-    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;                               // three chains of five: 20 instead of 60 cycles deep
-#pragma unroll
-    for (int pp = 0; pp < PE; pp += 3) {
-        a0 = cfma(tap[pp], x[pp], a0);
-        a1 = cfma(tap[pp + 1], x[pp + 1], a1);
-        a2 = cfma(tap[pp + 2], x[pp + 2], a2);
+    for (int b = 0; b < 3; b++) {
+        const float2 x0 = v[b], x1 = v[3 + b], x2 = v[6 + b], x3 = v[9 + b];
+        const float2 s02 = cadd(x0, x2), d02 = csub(x0, x2), s13 = cadd(x1, x3), d13 = mul_i(csub(x1, x3));
+        z[b][0] = cadd(s02, s13);
+        z[b][1] = cadd(d02, d13);
+        z[b][2] = csub(s02, s13);
+        z[b][3] = csub(d02, d13);
     }
-    return cadd(cadd(a0, a1), a2);
-}
-__device__ __forceinline__ float2 branch_sum_dyn(unsigned row0, const float2* __restrict__ col, const float (&tap)[PE]) {
-    switch (row0 & (RROWS - 1)) {       // warp-uniform up to the one column where the window wraps
-        case 0: return branch_sum<0>(col, tap);
-        case 1: return branch_sum<1>(col, tap);
-        case 2: return branch_sum<2>(col, tap);
-        case 3: return branch_sum<3>(col, tap);
-        case 4: return branch_sum<4>(col, tap);
-        case 5: return branch_sum<5>(col, tap);
-        case 6: return branch_sum<6>(col, tap);
-        case 7: return branch_sum<7>(col, tap);
-        case 8: return branch_sum<8>(col, tap);
-        case 9: return branch_sum<9>(col, tap);
-        case 10: return branch_sum<10>(col, tap);
-        case 11: return branch_sum<11>(col, tap);
-        case 12: return branch_sum<12>(col, tap);
-        case 13: return branch_sum<13>(col, tap);
-        case 14: return branch_sum<14>(col, tap);
-        default: return branch_sum<15>(col, tap);
+    // W12^1 = (c6, 1/2), W12^2 = (1/2, c6), W12^3 = i, W12^4 = (-1/2, c6), W12^6 = -1
+    z[1][1] = make_float2(c6 * z[1][1].x - 0.5f * z[1][1].y, c6 * z[1][1].y + 0.5f * z[1][1].x);
+    z[1][2] = make_float2(0.5f * z[1][2].x - c6 * z[1][2].y, 0.5f * z[1][2].y + c6 * z[1][2].x);
+    z[1][3] = mul_i(z[1][3]);
+    z[2][1] = make_float2(0.5f * z[2][1].x - c6 * z[2][1].y, 0.5f * z[2][1].y + c6 * z[2][1].x);
+    z[2][2] = make_float2(-0.5f * z[2][2].x - c6 * z[2][2].y, -0.5f * z[2][2].y + c6 * z[2][2].x);
+    z[2][3] = make_float2(-z[2][3].x, -z[2][3].y);
+#pragma unroll
+    for (int q1 = 0; q1 < 4; q1++) {
+        const float2 s = cadd(z[1][q1], z[2][q1]), d = csub(z[1][q1], z[2][q1]);
+        const float2 mid = make_float2(z[0][q1].x - 0.5f * s.x, z[0][q1].y - 0.5f * s.y);
+        const float2 rot = make_float2(-c6 * d.y, c6 * d.x);           // i * c6 * (z1 - z2)
+        v[q1] = cadd(z[0][q1], s);
+        v[q1 + 4] = cadd(mid, rot);
+        v[q1 + 8] = csub(mid, rot);
     }
 }
 
-__global__ void __launch_bounds__(NTX, 1) p25_pfbx_kernel(const PfbParams p, const unsigned times_per_cta) {
+// ten-term boxcar over d[i .. i + 9], i = 0..7, d = nine carried values ++ eight new, for the thread's two channels at
+// once (x = channel k', y = channel k' + 768): a tree of pair sums on the packed pipe
+__device__ __forceinline__ void boxcar8(const float2 (&hist)[9], const float2 (&dn)[TB], float2 (&out)[TB]) {
+    float2 d[17];
+#pragma unroll
+    for (int i = 0; i < 9; i++) d[i] = hist[i];
+#pragma unroll
+    for (int i = 0; i < TB; i++) d[9 + i] = dn[i];
+    float2 s2[16], s4[14], s8[8];
+#pragma unroll
+    for (int i = 0; i < 16; i++) s2[i] = cadd(d[i], d[i + 1]);
+#pragma unroll
+    for (int i = 0; i < 14; i++) s4[i] = cadd(s2[i], s2[i + 2]);
+#pragma unroll
+    for (int i = 0; i < 8; i++) s8[i] = cadd(s4[i], s4[i + 4]);
+#pragma unroll
+    for (int i = 0; i < TB; i++) {
+        const float2 t = cadd(s8[i], s2[i + 8]);
+        out[i] = make_float2(t.x * (1.0f / P25_BOXCAR), t.y * (1.0f / P25_BOXCAR));
+    }
+}
+
+// branch sum of one class with the newest sample in slot K: slot j holds the ((K - j) mod 16)-th newest sample
+template <int K>
+__device__ __forceinline__ float2 branch_sum(float2 (&win)[WS], const float4* __restrict__ row, bool adv, float2 nx0) {
+    if (adv) win[K] = nx0;
+    const float4 t0 = row[0], t1 = row[ROWS], t2 = row[2 * ROWS], t3 = row[3 * ROWS];
+    const float tap[WS] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w, t3.x, t3.y, t3.z, t3.w};
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+    for (int j = 0; j < WS; j += 4) {
+        a0 = cfma(tap[(K - j) & 15], win[j], a0);
+        a1 = cfma(tap[(K - j - 1) & 15], win[j + 1], a1);
+        a2 = cfma(tap[(K - j - 2) & 15], win[j + 2], a2);
+        a3 = cfma(tap[(K - j - 3) & 15], win[j + 3], a3);
+    }
+    return cadd(cadd(a0, a1), cadd(a2, a3));
+}
+#define P25_PFB_CASE(k) \
+    case k: sum = branch_sum<k>(win[cc], row, adv, nx[cc][0]); break;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_kernel(const PfbParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemX& sm = *reinterpret_cast<SmemX*>(smem_raw);
-    const int tid = threadIdx.x;
-    const unsigned cap = blockIdx.y;
-    const int t_first = (int)(blockIdx.x * times_per_cta);       // this CTA's consecutive output times, relative to m0
-    const int t_last = min(t_first + (int)times_per_cta, (int)p.n_out);
-    if (t_first >= t_last) return;
+    SmemC& sm = *reinterpret_cast<SmemC*>(smem_raw);
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = (int)cluster.block_rank();                      // parity of the FFT inputs / classes this CTA owns
+    const unsigned run = blockIdx.x >> 1;
+    const unsigned cap = run / p.runs_per_cap;
+    const int t_first = (int)((run % p.runs_per_cap) * p.times_per_run);          // relative to m0, a multiple of TB
+    const int t_last = min(t_first + (int)p.times_per_run, (int)p.n_out);
+    if (cap >= p.n_captures || t_first >= t_last) return;         // both CTAs of the cluster take the same way out
     const float2* chunk = p.iq + (size_t)cap * p.n;
     const float2* tail = p.tail_in + (size_t)cap * HTX;
-    if (tid < N / 8) sm.tw192[tid] = p.twiddle[tid];
-    if (tid < 24) sm.tw24[tid] = p.twiddle[8 * tid];
-    if (tid < 3) sm.tw3[tid] = p.twiddle[64 * tid];
-    float tap[3][PE];
-#pragma unroll
-    for (int b = 0; b < 3; b++)
-#pragma unroll
-        for (int pp = 0; pp < PE; pp++) tap[b][pp] = __ldg(p.taps + tid + NTX * b + N * pp);
-    // logical index (tail ++ chunk, tail = HTX samples) of the newest input of output time t: n_m - a0 + HTX
-    const long long e_base = (long long)M * (long long)p.m0 + (M - 1) - (long long)p.a0 + HTX;
-    {   // the window of the warm-up output time t_first - 1
-        const long long e0 = e_base + (long long)M * (t_first - 1);
-        for (int i = tid; i < LE; i += NTX) {
-            const long long l = e0 - (LE - 1) + i;
-            sm.ring[(int)((l + 4ll * RING) % RING)] = load_logical(p, tail, chunk, l);
-        }
+    const int n_in = (int)p.n;
+    const unsigned inc_remote = map_to_rank(smem_u32(&sm.inc[0][0][0]), (unsigned)(b ^ 1));
+    const unsigned mbar_remote = map_to_rank(smem_u32(&sm.mbar[0]), (unsigned)(b ^ 1));
+    constexpr unsigned INC_BYTES = TB * (H / 2) * sizeof(float2);             // one batch of the partner's half
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.mbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.mbar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    float2 nx = make_float2(0.f, 0.f);                            // next output time's new samples, one per thread (M <= NTX)
-    if (tid < M) nx = load_logical(p, tail, chunk, e_base + (long long)M * (t_first - 1) + 1 + tid);
-    float2 cprev[8];
-    float pw[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        cprev[r] = make_float2(0.f, 0.f);
-        pw[r] = 0.f;
-    }
-    float* dcap = p.d + ((size_t)cap * p.d_rows + DHIST) * N;
 
-    for (int t = t_first - 1; t < t_last; t++) {
-        __syncthreads();                                          // ring holds the window of t; fa / fb are free
-        const long long e = e_base + (long long)M * t;            // > LE by construction (HTX >= LE + M - 1)
-        const long long n_m = (long long)M * ((long long)p.m0 + t) + (M - 1);
-        const int nm_mod = (int)(((n_m % N) + N) % N);
-        // branches: v[r] = sum_p heq[r + N p] * x[n_m - r - N p], stored at q = (r - n_m) mod N
+    for (int i = tid; i < 4 * ROWS; i += NTH) {
+        const int g = i / ROWS, row = i - g * ROWS;
+        const int d0 = 2 * row - EARLY + (1 - b);
+        float t[4];
 #pragma unroll
-        for (int b = 0; b < 3; b++) {
-            const int r = tid + NTX * b;
-            const unsigned J = (unsigned)(e - r);
-            const unsigned row0 = J / N, col = J - row0 * N;
-            const float2 acc = branch_sum_dyn(row0, sm.ring + col, tap[b]);
-            int q = r - nm_mod;
-            if (q < 0) q += N;
-            sm.fa[q] = acc;
+        for (int kk = 0; kk < 4; kk++) {
+            const int idx = d0 + N * (4 * g + kk);
+            t[kk] = (idx >= 0 && idx < LE) ? __ldg(p.taps + idx) : 0.f;
         }
-        __syncthreads();                                          // window consumed, fa complete
-        if (tid < M && t + 1 < t_last) sm.ring[(int)((e + 1 + tid) % RING)] = nx;     // slots older than the next window
-        if (tid < M && t + 2 < t_last) nx = load_logical(p, tail, chunk, e + M + 1 + tid);
-        // radix-3 pass (NS = 1): 512 butterflies, one per thread
-        {
-            const int j = tid;
-            const float2 a = sm.fa[j], bb = sm.fa[j + N / 3], c = sm.fa[j + 2 * (N / 3)];
-            const float s3 = 0.86602540378443865f;
-            const float2 bc = cadd(bb, c), dd = csub(bb, c);
-            const float2 mid = make_float2(a.x - 0.5f * bc.x, a.y - 0.5f * bc.y);
-            const float2 rot = make_float2(-s3 * dd.y, s3 * dd.x);          // i * s3 * (b - c)
-            sm.fb[3 * j] = cadd(a, bc);
-            sm.fb[3 * j + 1] = cadd(mid, rot);                             // a + b w + c w^2, w = exp(+2 pi i / 3)
-            sm.fb[3 * j + 2] = csub(mid, rot);
+        sm.tab[g][row] = make_float4(t[0], t[1], t[2], t[3]);
+    }
+    if (tid < 64) sm.twB[tid] = p.twiddle[24 * (tid >> 3) * (tid & 7)];
+    for (int i = tid; i < 12 * 64; i += NTH) sm.twC[i >> 6][i & 63] = p.twiddle[2 * (i >> 6) * (i & 63)];
+    const int k2 = H / 2 * b + tid;                                // this thread's channels: k2 and k2 + 768
+    const float2 wk = p.twiddle[k2];
+
+    // ---- window state of the two classes, describing output time t_first - WARM - 1
+    // logical index (tail ++ chunk, tail = HTX samples) of n_m for t = 0; every index below fits 32 bits (n <= 2^30)
+    const int e_base = (int)((long long)M * (long long)p.m0 + (M - 1) - (long long)p.a0) + HTX;
+    float2 win[2][WS], nx[2][3];
+    int d0[2], phi[2];
+    const int lim = N - M - 2 * (31 - lane);                       // the warp's last lane reaches d0 >= N at the next output time
+    {
+        const int e_init = e_base + M * (t_first - WARM - 1);
+        const int a0m = (int)(p.a0 % (unsigned long long)N);
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int u = tid + NTH * cc;
+            const int c = (N - (2 * u + b)) % N;                  // residue class of the samples behind FFT input q = 2 u + b
+            const int cl = (c + HTX % N + N - a0m) % N;           // ... as a residue of the logical index
+            const int rp = (e_init - cl) % N;                     // distance back to the class's latest sample (e_init >= N)
+            const int rp0 = __shfl_sync(0xffffffffu, rp, 0);
+            // lane i sits 2 i inputs below lane 0; if the warp's last lane would already be a whole N behind, the warp
+            // starts one sample ahead (its first lanes then hold an early sample)
+            d0[cc] = rp0 + 2 * lane - (rp0 + 62 >= N ? N : 0);
+            phi[cc] = 0;
+            const int lnew = e_init - d0[cc];
+#pragma unroll
+            for (int kk = 0; kk < WS; kk++) win[cc][(WS - kk) & 15] = load_logical(tail, chunk, n_in, lnew - N * kk);
         }
-        __syncthreads();
-        if (tid < N / 8) pass8x<3>(sm.fb, sm.fa, sm.tw3[tid % 3], tid);
-        __syncthreads();
-        if (tid < N / 8) pass8x<24>(sm.fa, sm.fb, sm.tw24[tid % 24], tid);
-        __syncthreads();
-        if (tid < N / 8) {
-            // last pass (NS = 192) in registers: thread j ends up with channels k = j + 192 r, the same at every time
-            const int j = tid;
-            float2 v[8], w[8];
+    }
 #pragma unroll
-            for (int r = 0; r < 8; r++) v[r] = sm.fb[j + r * (N / 8)];
-            powers7(sm.tw192[j], w);
+    for (int cc = 0; cc < 2; cc++)                                 // the samples the classes receive during the first batch
 #pragma unroll
-            for (int r = 1; r < 8; r++) v[r] = cmul(v[r], w[r]);
-            dft8(v);
-            if (t >= t_first) {
-                float* drow = dcap + (size_t)t * N;
+        for (int i = 0; i < 3; i++)
+            nx[cc][i] = load_logical(tail, chunk, n_in, e_base + M * (t_first - WARM - 1) - d0[cc] + N * (i + 1));
+    float2 cprev[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    float2 hist[9];                                                // x: channel k2, y: channel k2 + 768
+    float pw[2] = {0.f, 0.f};
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    const float2 cur = v[r], prv = cprev[r];
-                    const float re = cur.x * prv.x + cur.y * prv.y;
-                    const float im = cur.y * prv.x - cur.x * prv.y;
-                    drow[j + r * (N / 8)] = atan2_branchfree(im, re) * P25_FM_GAIN;
-                    pw[r] += cur.x * cur.x + cur.y * cur.y;
+    for (int i = 0; i < 9; i++) hist[i] = make_float2(0.f, 0.f);
+    float* const out_lo = p.bb + ((size_t)cap * N + k2) * p.row_stride + P25CU_BB_HIST;
+    float* const out_hi = out_lo + (size_t)H * p.row_stride;
+    const int t_begin = t_first - WARM;                            // first output time that is computed
+    cluster.sync();                                                // both CTAs' barriers are initialised before either one sends
+
+    unsigned nb = 0;                                               // batch counter: incoming buffer nb & 1, phase (nb >> 1) & 1
+    for (int tb = t_first - 2 * TB; tb < t_last; tb += TB, nb++) {
+        if (tid == 0) mbar_expect_tx(smem_u32(&sm.mbar[nb & 1]), INC_BYTES);
+        const int tt_lo = max(t_begin - tb, 0), tt_hi = min(t_last - tb, TB);      // active output times of this batch
+        // ---- polyphase branch sums of up to eight output times
+#pragma unroll 1
+        for (int tt = tt_lo; tt < tt_hi; tt++) {
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+                const bool adv = d0[cc] >= lim;                    // warp-uniform
+                d0[cc] += adv ? M - N : M;
+                phi[cc] = (phi[cc] + (adv ? 1 : 0)) & 15;
+                const float4* row = &sm.tab[0][(d0[cc] + EARLY) >> 1];
+                float2 sum;
+                switch (phi[cc]) {
+                    P25_PFB_CASE(0) P25_PFB_CASE(1) P25_PFB_CASE(2) P25_PFB_CASE(3) P25_PFB_CASE(4) P25_PFB_CASE(5)
+                    P25_PFB_CASE(6) P25_PFB_CASE(7) P25_PFB_CASE(8) P25_PFB_CASE(9) P25_PFB_CASE(10) P25_PFB_CASE(11)
+                    P25_PFB_CASE(12) P25_PFB_CASE(13) P25_PFB_CASE(14)
+                    default: sum = branch_sum<15>(win[cc], row, adv, nx[cc][0]); break;
                 }
-                if (p.y) {
-                    float2* yrow = p.y + ((size_t)cap * p.y_rows + t) * N;
+                if (adv) {
+                    nx[cc][0] = nx[cc][1];
+                    nx[cc][1] = nx[cc][2];
+                }
+                sm.f0[tt][tid + NTH * cc] = sum;
+            }
+        }
+        // the (at most three) samples each class receives during the NEXT batch: in flight behind the FFT passes
+        if (tb + TB < t_last) {
+            const int e_now = e_base + M * (tb + TB - 1);          // the windows describe this output time
 #pragma unroll
-                    for (int r = 0; r < 8; r++) yrow[j + r * (N / 8)] = v[r];
+            for (int cc = 0; cc < 2; cc++)
+#pragma unroll
+                for (int i = 0; i < 3; i++) nx[cc][i] = load_logical(tail, chunk, n_in, e_now - d0[cc] + N * (i + 1));
+        }
+        __syncthreads();
+        // ---- pass A: radix 8, stride 1, no twiddles; in place (read, barrier, write skewed)
+        {
+            float2 v[2][8];
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const int item = tid + NTH * rr, tt = item / 96, j = item - 96 * tt;
+#pragma unroll
+                for (int r = 0; r < 8; r++) v[rr][r] = sm.f0[tt][j + 96 * r];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const int item = tid + NTH * rr, tt = item / 96, j = item - 96 * tt;
+                dft8(v[rr]);
+#pragma unroll
+                for (int q = 0; q < 8; q++) sm.f0[tt][skew(8 * j + q)] = v[rr][q];
+            }
+        }
+        __syncthreads();
+        // ---- pass B: radix 8, stride 8
+        {
+            float2 v[2][8];
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const int item = tid + NTH * rr, tt = item / 96, j = item - 96 * tt;
+#pragma unroll
+                for (int r = 0; r < 8; r++) v[rr][r] = sm.f0[tt][skew(j + 96 * r)];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const int item = tid + NTH * rr, tt = item / 96, j = item - 96 * tt, k = j & 7;
+#pragma unroll
+                for (int r = 1; r < 8; r++) v[rr][r] = cmul(v[rr][r], sm.twB[8 * k + r]);
+                dft8(v[rr]);
+                const int j0 = (j >> 3) * 64 + k;
+#pragma unroll
+                for (int q = 0; q < 8; q++) sm.f0[tt][skew(j0 + 8 * q)] = v[rr][q];
+            }
+        }
+        __syncthreads();
+        // ---- pass C: radix 12, stride 64.  Outputs k' = j + 64 q: q < 6 lies in CTA 0's combine range, q >= 6 in CTA 1's;
+        // the half this CTA combines itself stays here, the other goes straight into the partner's incoming buffer.  The
+        // partner cannot still be reading that buffer: it holds the batch before last, and the partner's data of the last
+        // batch -- sent after it had finished with that one -- has already been consumed here.
+#pragma unroll 1
+        for (int rr = 0; rr < 2; rr++) {
+            const int item = tid + NTH * rr;
+            if (item >= TB * 64) break;
+            const int tt = item >> 6, j = item & 63;
+            float2 v[12];
+            v[0] = sm.f0[tt][skew(j)];
+#pragma unroll
+            for (int r = 1; r < 12; r++) v[r] = cmul(sm.f0[tt][skew(j + 64 * r)], sm.twC[r][j]);
+            dft12(v);
+            const unsigned rbase = inc_remote + (unsigned)((((nb & 1) * TB + tt) * (H / 2) + j) * sizeof(float2));
+            const unsigned rmbar = mbar_remote + (unsigned)((nb & 1) * sizeof(unsigned long long));
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+                const float2 mine = b == 0 ? v[q] : v[q + 6], theirs = b == 0 ? v[q + 6] : v[q];
+                sm.own[tt][j + 64 * q] = mine;
+                st_async_f2(rbase + (unsigned)(64 * q * sizeof(float2)), theirs, rmbar);
+            }
+        }
+        __syncthreads();                                           // own[] complete
+        mbar_wait(smem_u32(&sm.mbar[nb & 1]), (nb >> 1) & 1);      // ... and all of the partner's half has landed
+        // ---- radix-2 combine across the pair, discriminator, boxcar, baseband rows: two channels per thread
+        float2 ge[TB], go[TB];
+#pragma unroll
+        for (int tt = 0; tt < TB; tt++) {
+            const float2 mine = sm.own[tt][tid], theirs = sm.inc[nb & 1][tt][tid];
+            ge[tt] = b == 0 ? mine : theirs;
+            go[tt] = b == 0 ? theirs : mine;
+        }
+        float2 dn[TB];
+        const bool full = tt_lo == 0 && tt_hi == TB && tb >= t_first;          // the common case: no per-time tests
+#pragma unroll
+        for (int tt = 0; tt < TB; tt++) {
+            const int t = tb + tt;
+            dn[tt] = make_float2(0.f, 0.f);
+            if (full || (tt >= tt_lo && tt < tt_hi)) {
+                const float2 wo = cmul(wk, go[tt]);
+                const float2 cur[2] = {cadd(ge[tt], wo), csub(ge[tt], wo)};
+                float dd[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float re = cur[h].x * cprev[h].x + cur[h].y * cprev[h].y;
+                    const float im = cur[h].y * cprev[h].x - cur[h].x * cprev[h].y;
+                    dd[h] = atan2_branchfree(im, re) * P25_FM_GAIN;
+                    cprev[h] = cur[h];
+                }
+                dn[tt] = make_float2(dd[0], dd[1]);
+                if (full || t >= t_first) {
+                    pw[0] += cur[0].x * cur[0].x + cur[0].y * cur[0].y;
+                    pw[1] += cur[1].x * cur[1].x + cur[1].y * cur[1].y;
+                    if (p.y) {
+                        float2* yrow = p.y + ((size_t)cap * p.y_rows + t) * N;
+                        yrow[k2] = cur[0];
+                        yrow[k2 + H] = cur[1];
+                    }
                 }
             }
+        }
+        {
+            float2 box[TB];
+            boxcar8(hist, dn, box);
+            hist[0] = hist[8];
 #pragma unroll
-            for (int r = 0; r < 8; r++) cprev[r] = v[r];
+            for (int i = 0; i < TB; i++) hist[1 + i] = dn[i];
+            if (full) {
+                *reinterpret_cast<float4*>(out_lo + tb) = make_float4(box[0].x, box[1].x, box[2].x, box[3].x);
+                *reinterpret_cast<float4*>(out_lo + tb + 4) = make_float4(box[4].x, box[5].x, box[6].x, box[7].x);
+                *reinterpret_cast<float4*>(out_hi + tb) = make_float4(box[0].y, box[1].y, box[2].y, box[3].y);
+                *reinterpret_cast<float4*>(out_hi + tb + 4) = make_float4(box[4].y, box[5].y, box[6].y, box[7].y);
+            } else {
+#pragma unroll
+                for (int i = 0; i < TB; i++)
+                    if (tb + i >= t_first && tb + i < t_last) {
+                        out_lo[tb + i] = box[i].x;
+                        out_hi[tb + i] = box[i].y;
+                    }
+            }
         }
     }
-    if (p.power_sum && tid < N / 8) {
-#pragma unroll
-        for (int r = 0; r < 8; r++) atomicAdd(p.power_sum + (size_t)cap * N + tid + r * (N / 8), pw[r]);
+    cluster.sync();                                                // neither CTA leaves while the other may still send to it
+    if (p.power_sum) {
+        atomicAdd(p.power_sum + (size_t)cap * N + k2, pw[0]);
+        atomicAdd(p.power_sum + (size_t)cap * N + k2 + H, pw[1]);
     }
 }
-
-// ------------------------------------------------------------------------------------------------ kernel B
-// Boxcar over ten discriminator samples (oldest first, like the oracle) and transpose: a CTA takes 32 channels x 128
-// output times of d (128-byte row segments), every warp then writes 32 consecutive times of one channel's baseband row.
-constexpr int KC = 32;                 // channels per CTA
-constexpr int TB = 128;                // output times per CTA
-
-struct SmemB {
-    float dt[TB + DHIST][KC + 1];
-};
-
-struct ChanParams {
-    const float* d;            // [captures][d_rows][N]; row DHIST + t = output time t of this chunk, rows 0 .. DHIST-1 carried
-    float* bb;                 // baseband rows, stream = capture * N + channel
-    size_t row_stride;
-    unsigned n_out, n_captures, d_rows;
-};
-
-__global__ void __launch_bounds__(256) p25_chan_box_kernel(const ChanParams p) {
-    __shared__ SmemB sm;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned cap = blockIdx.z, k0 = blockIdx.y * KC;
-    const int t0 = blockIdx.x * TB;
-    const float* dc = p.d + (size_t)cap * p.d_rows * N;
-    for (int i = warp; i < TB + DHIST; i += 8) {
-        const int t = t0 - DHIST + i;                              // row DHIST + t
-        sm.dt[i][lane] = t < (int)p.n_out ? __ldg(dc + (size_t)(DHIST + t) * N + k0 + lane) : 0.f;
-    }
-    __syncthreads();
-    for (int ch = warp; ch < KC; ch += 8) {
-        float* out = p.bb + ((size_t)cap * N + k0 + ch) * p.row_stride + P25CU_BB_HIST;
-        for (int o = lane; o < TB; o += 32) {
-            const int t = t0 + o;
-            if (t >= (int)p.n_out) break;
-            float acc = 0.f;
-#pragma unroll
-            for (int i = 0; i < P25_BOXCAR; i++) acc += sm.dt[o + i][ch];
-            out[t] = acc * (1.0f / P25_BOXCAR);
-        }
-    }
-}
+#undef P25_PFB_CASE
 
 // carried input tail: tail_out[i] = logical[n + i], logical = tail_in ++ chunk (both cf32), i < HTX
 __global__ void p25_pfb_tail_kernel(const float2* iq, const float2* tail_in, float2* tail_out, unsigned n) {
@@ -369,7 +544,6 @@ __global__ void p25_pfb_tail_kernel(const float2* iq, const float2* tail_in, flo
 unsigned p25cu_pfb_tail_len() { return (unsigned)pfb::HTX; }
 unsigned p25cu_pfb_channels() { return (unsigned)pfb::N; }
 unsigned p25cu_pfb_decimation() { return (unsigned)pfb::M; }
-unsigned p25cu_pfb_hist_rows() { return (unsigned)pfb::DHIST; }
 
 // Equivalent prototype heq = hp (*) upsample(hc, M), in double, rounded once to f32; twiddle table.
 cudaError_t p25cu_pfb_upload(float** d_taps, float2** d_twiddle) {
@@ -397,15 +571,26 @@ cudaError_t p25cu_pfb_upload(float** d_taps, float2** d_twiddle) {
 
 // Per-device setup (once per device under the library's plan mutex, that device current).
 cudaError_t p25cu_pfb_plan_device(P25DevPlan* plan) {
-    cudaError_t e = cudaFuncSetAttribute(pfb::p25_pfbx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pfb::SmemX));
+    cudaError_t e = cudaFuncSetAttribute(pfb::p25_pfbc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(pfb::SmemC));
     if (e != cudaSuccess) return e;
-    plan->pfb_slots = plan->n_sm;          // one 222 KB CTA per SM
+    // clusters of two 200 KB CTAs that can be resident at once (at most one per SM pair of a GPC)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * plan->n_sm);
+    cfg.blockDim = dim3(pfb::NTH);
+    cfg.dynamicSmemBytes = sizeof(pfb::SmemC);
+    int n_clusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&n_clusters, pfb::p25_pfbc_kernel, &cfg);
+    if (e != cudaSuccess || n_clusters < 1) {
+        (void)cudaGetLastError();
+        n_clusters = plan->n_sm / 2;
+    }
+    plan->pfb_slots = n_clusters;
     return cudaSuccess;
 }
 
-// One chunk of every capture: discriminator rows into d (rows DHIST ..), baseband rows into bb, new tail.
-cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out, const float* taps, const float2* twiddle, float* d,
-                             unsigned d_rows, float2* y, unsigned y_rows, float* bb, size_t row_stride, float* power_sum,
+// One chunk of every capture: baseband rows into bb, new tail.
+cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out, const float* taps, const float2* twiddle,
+                             float2* y, unsigned y_rows, float* bb, size_t row_stride, float* power_sum,
                              unsigned long long a0, unsigned long long m0, unsigned n, unsigned n_out, unsigned n_captures,
                              cudaStream_t st, unsigned* launches, const P25DevPlan* plan) {
     if (n_out) {
@@ -414,7 +599,8 @@ cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out
         a.tail_in = (const float2*)tail_in;
         a.taps = taps;
         a.twiddle = twiddle;
-        a.d = d;
+        a.bb = bb;
+        a.row_stride = row_stride;
         a.y = y;
         a.power_sum = power_sum;
         a.a0 = a0;
@@ -422,26 +608,18 @@ cudaError_t p25cu_launch_pfb(const void* iq, const void* tail_in, void* tail_out
         a.n = n;
         a.n_out = n_out;
         a.n_captures = n_captures;
-        a.d_rows = d_rows;
         a.y_rows = y_rows;
-        // one wave: every SM gets one run of consecutive output times (each run pays one window fill and one warm-up
-        // output time), the captures share the SMs evenly
+        // one wave: every resident cluster gets one run of consecutive output times (each run pays the table load and
+        // ten warm-up output times), the captures share the clusters evenly; runs are whole batches of eight
         unsigned per_cap = (unsigned)plan->pfb_slots / n_captures;
         if (per_cap < 1) per_cap = 1;
-        unsigned tpc = (n_out + per_cap - 1) / per_cap;                  // output times per CTA
-        if (tpc < 8) tpc = n_out < 8 ? n_out : 8;
-        const dim3 ga((n_out + tpc - 1) / tpc, n_captures);
-        pfb::p25_pfbx_kernel<<<ga, pfb::NTX, sizeof(pfb::SmemX), st>>>(a, tpc);
-        pfb::ChanParams b;
-        b.d = d;
-        b.bb = bb;
-        b.row_stride = row_stride;
-        b.n_out = n_out;
-        b.n_captures = n_captures;
-        b.d_rows = d_rows;
-        const dim3 gb((n_out + pfb::TB - 1) / pfb::TB, pfb::N / pfb::KC, n_captures);
-        pfb::p25_chan_box_kernel<<<gb, 256, 0, st>>>(b);
-        *launches += 2;
+        unsigned tpr = (n_out + per_cap - 1) / per_cap;
+        tpr = (tpr + pfb::TB - 1) / pfb::TB * pfb::TB;
+        if (tpr < 4 * pfb::TB) tpr = 4 * pfb::TB;                          // keep the warm-up share below a third
+        a.times_per_run = tpr;
+        a.runs_per_cap = (n_out + tpr - 1) / tpr;
+        pfb::p25_pfbc_kernel<<<2 * a.runs_per_cap * n_captures, pfb::NTH, sizeof(pfb::SmemC), st>>>(a);
+        *launches += 1;
     }
     if (n) {
         const dim3 gt((pfb::HTX + 255) / 256, n_captures);

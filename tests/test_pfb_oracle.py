@@ -77,3 +77,27 @@ def test_channel_carries_a_decodable_control_channel():
         assert S.crc_ccitt_p25(pl[:10]) == (pl[10] << 8 | pl[11])
     quiet = o.MessageReceiver().feed(o.DemodChain(o.FMT_CF32, 2).feed(y[:, 900].astype(np.complex64)))
     assert len(quiet) == 0
+
+
+def test_kernel_dataflow_equals_the_definition():
+    """spec/pfb_dataflow.py restates the index arithmetic of p25_pfbc_kernel (register windows per residue class that
+    advance a warp at a time, tap rows by distance to the newest sample, parity split over the two CTAs of a cluster, 8 x 8 x 12 Stockham passes, radix-2 combine, warm-up from the
+    carried tail).  Three unequal chunks, odd lengths: every output time equals the fused float64 oracle."""
+    import pfb_dataflow as df
+    src = open(os.path.join(ROOT, "p25rx_b200", "csrc", "pfb.cu")).read()
+    for name in ("HTX", "WARM", "TB", "NTH", "WS", "EARLY"):       # the model and the kernel agree on their constants
+        assert int(re.search(rf"constexpr int {name} = (\d+);", src).group(1)) == getattr(df, name), name
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(768) + 1j * rng.standard_normal(768)
+    assert np.max(np.abs(df.idft768(v) - np.fft.ifft(v) * 768)) < 1e-10
+    heq = po.equivalent_prototype()
+    x = rng.standard_normal(36 * 400 + 123) + 1j * rng.standard_normal(36 * 400 + 123)
+    ref = po.channelize_fused(x)
+    tail, pos = np.zeros(df.HTX, dtype=np.complex128), 0
+    for n in (5001, 6777, len(x) - 5001 - 6777):
+        m0 = max(0, -(-(pos - 399) // 400))                # first output whose newest input lies in this chunk
+        n_out = (pos + n - 400) // 400 - m0 + 1
+        y = df.Run(heq, tail, x[pos:pos + n], pos, m0).spectra(0, n_out)[df.WARM:]
+        assert np.max(np.abs(y - ref[m0:m0 + n_out])) < 1e-12 * np.max(np.abs(ref))
+        tail = np.concatenate([tail, x[pos:pos + n]])[-df.HTX:]
+        pos += n
