@@ -53,6 +53,16 @@ __device__ __forceinline__ float2 cfma(float h, float2 x, float2 acc) {
     return *reinterpret_cast<float2*>(&r);
 }
 
+// a * w for a twiddle kept as {w, i w} = {w.x, w.y, -w.y, w.x}: a.x * w + a.y * (i w), one FMUL2 + one FFMA2 (the scalar
+// factor rides in the packed instructions' broadcast operand)
+__device__ __forceinline__ float2 cmulw(float2 a, float4 w) {
+    unsigned long long r;
+    const float2 ax = make_float2(a.x, a.x), w0 = make_float2(w.x, w.y);
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const unsigned long long*>(&ax)), "l"(*reinterpret_cast<const unsigned long long*>(&w0)));
+    return cfma(a.y, make_float2(w.z, w.w), *reinterpret_cast<float2*>(&r));
+}
+__device__ __forceinline__ float4 twiddle4(float2 w) { return make_float4(w.x, w.y, -w.y, w.x); }
+
 // 8-point DFT with the + sign: w[q] = sum_r v[r] exp(+2 pi i r q / 8), in place
 __device__ __forceinline__ void dft8(float2 (&v)[8]) {
     const float h = 0.70710678118654752f;
@@ -154,8 +164,8 @@ struct SmemC {
     float2 own[TB][H / 2];             // this CTA's transform at the 384 k' it combines itself
     float2 inc[2][TB][H / 2];          // the partner's transform at the same k', written by the partner (st.async), two batches deep
     unsigned long long mbar[2];        // one transaction barrier per incoming buffer
-    float2 twB[64];                    // exp(+2 pi i k r / 64) at [8 k + r]
-    float2 twC[12][64];                // exp(+2 pi i j r / 768) at [r][j]
+    float4 twB[8][8];                  // w = exp(+2 pi i k r / 64) at [r][k], as {w, i w} (cmulw)
+    float4 twC[12][64];                // w = exp(+2 pi i j r / 768) at [r][j]
 };
 
 struct PfbParams {
@@ -263,24 +273,54 @@ __device__ __forceinline__ void boxcar8(const float2 (&hist)[9], const float2 (&
     }
 }
 
-// branch sum of one class with the newest sample in slot K: slot j holds the ((K - j) mod 16)-th newest sample
-template <int K>
-__device__ __forceinline__ float2 branch_sum(float2 (&win)[WS], const float4* __restrict__ row, bool adv, float2 nx0) {
-    if (adv) win[K] = nx0;
-    const float4 t0 = row[0], t1 = row[ROWS], t2 = row[2 * ROWS], t3 = row[3 * ROWS];
-    const float tap[WS] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w, t3.x, t3.y, t3.z, t3.w};
-    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+// Radix-2 combine of one output time (channels k' and k' + 768 from E[k'], O[k'], w^k'), FM discriminator against the
+// previous output time (src/demod.rs:109-111) and power (src/demod.rs:95-101); cprev is left at this time's spectra.
+__device__ __forceinline__ float2 combine_disc(float2 e, float2 o, float4 wk, float2 (&cprev)[2], float (&pw)[2]) {
+    const float2 wo = cmulw(o, wk);
+    const float2 cur[2] = {cadd(e, wo), csub(e, wo)};
+    float dd[2];
 #pragma unroll
-    for (int j = 0; j < WS; j += 4) {
-        a0 = cfma(tap[(K - j) & 15], win[j], a0);
-        a1 = cfma(tap[(K - j - 1) & 15], win[j + 1], a1);
-        a2 = cfma(tap[(K - j - 2) & 15], win[j + 2], a2);
-        a3 = cfma(tap[(K - j - 3) & 15], win[j + 3], a3);
+    for (int h = 0; h < 2; h++) {
+        const float re = cur[h].x * cprev[h].x + cur[h].y * cprev[h].y;
+        const float im = cur[h].y * cprev[h].x - cur[h].x * cprev[h].y;
+        dd[h] = atan2_branchfree(im, re) * P25_FM_GAIN;
+        pw[h] += cur[h].x * cur[h].x + cur[h].y * cur[h].y;
+        cprev[h] = cur[h];
     }
-    return cadd(cadd(a0, a1), cadd(a2, a3));
+    return make_float2(dd[0], dd[1]);
+}
+
+// The output times of one class from this one up to (not including) the next window advance, or the end of the batch:
+// the newest sample stays in slot K, slot j holds the ((K - j) mod 16)-th newest, consecutive times differ only in the
+// tap row (d0 grows by M: M / 2 rows on).  Warp-uniform control flow throughout.
+template <int K>
+__device__ __forceinline__ void branch_run(float2 (&win)[WS], bool adv, float2 nx0, const float4* __restrict__ tab, float2* __restrict__ out,
+                                           int& d0, int& tt, int tt_hi, int lim) {
+    if (adv) win[K] = nx0;
+    const float4* row = tab + ((d0 + EARLY) >> 1);
+    out += tt * FSK;
+#pragma unroll 1
+    for (;;) {
+        const float4 t0 = row[0], t1 = row[ROWS], t2 = row[2 * ROWS], t3 = row[3 * ROWS];
+        const float tap[WS] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w, t3.x, t3.y, t3.z, t3.w};
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+        for (int j = 0; j < WS; j += 4) {
+            a0 = cfma(tap[(K - j) & 15], win[j], a0);
+            a1 = cfma(tap[(K - j - 1) & 15], win[j + 1], a1);
+            a2 = cfma(tap[(K - j - 2) & 15], win[j + 2], a2);
+            a3 = cfma(tap[(K - j - 3) & 15], win[j + 3], a3);
+        }
+        *out = cadd(cadd(a0, a1), cadd(a2, a3));
+        tt++;
+        if (tt >= tt_hi || d0 >= lim) break;                       // batch done, or the next output time advances the window
+        d0 += M;
+        row += M / 2;
+        out += FSK;
+    }
 }
 #define P25_PFB_CASE(k) \
-    case k: sum = branch_sum<k>(win[cc], row, adv, nx[cc][0]); break;
+    case k: branch_run<k>(win[cc], adv, nx0, &sm.tab[0][0], &sm.f0[0][tid + NTH * cc], d0[cc], tt, tt_hi, lim); break;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_kernel(const PfbParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -316,10 +356,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_ker
         }
         sm.tab[g][row] = make_float4(t[0], t[1], t[2], t[3]);
     }
-    if (tid < 64) sm.twB[tid] = p.twiddle[24 * (tid >> 3) * (tid & 7)];
-    for (int i = tid; i < 12 * 64; i += NTH) sm.twC[i >> 6][i & 63] = p.twiddle[2 * (i >> 6) * (i & 63)];
+    if (tid < 64) sm.twB[tid >> 3][tid & 7] = twiddle4(p.twiddle[24 * (tid >> 3) * (tid & 7)]);
+    for (int i = tid; i < 12 * 64; i += NTH) sm.twC[i >> 6][i & 63] = twiddle4(p.twiddle[2 * (i >> 6) * (i & 63)]);
     const int k2 = H / 2 * b + tid;                                // this thread's channels: k2 and k2 + 768
-    const float2 wk = p.twiddle[k2];
+    const float4 wk = twiddle4(p.twiddle[k2]);
 
     // ---- window state of the two classes, describing output time t_first - WARM - 1
     // logical index (tail ++ chunk, tail = HTX samples) of n_m for t = 0; every index below fits 32 bits (n <= 2^30)
@@ -365,36 +405,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_ker
     for (int tb = t_first - 2 * TB; tb < t_last; tb += TB, nb++) {
         if (tid == 0) mbar_expect_tx(smem_u32(&sm.mbar[nb & 1]), INC_BYTES);
         const int tt_lo = max(t_begin - tb, 0), tt_hi = min(t_last - tb, TB);      // active output times of this batch
-        // ---- polyphase branch sums of up to eight output times
-#pragma unroll 1
-        for (int tt = tt_lo; tt < tt_hi; tt++) {
+        // ---- polyphase branch sums of up to eight output times, one class after the other
 #pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
+        for (int cc = 0; cc < 2; cc++) {
+            int tt = tt_lo;
+#pragma unroll 1
+            while (tt < tt_hi) {
                 const bool adv = d0[cc] >= lim;                    // warp-uniform
                 d0[cc] += adv ? M - N : M;
-                phi[cc] = (phi[cc] + (adv ? 1 : 0)) & 15;
-                const float4* row = &sm.tab[0][(d0[cc] + EARLY) >> 1];
-                float2 sum;
+                const float2 nx0 = nx[cc][0];
+                if (adv) {
+                    phi[cc] = (phi[cc] + 1) & 15;
+                    nx[cc][0] = nx[cc][1];
+                    nx[cc][1] = nx[cc][2];
+                }
                 switch (phi[cc]) {
                     P25_PFB_CASE(0) P25_PFB_CASE(1) P25_PFB_CASE(2) P25_PFB_CASE(3) P25_PFB_CASE(4) P25_PFB_CASE(5)
                     P25_PFB_CASE(6) P25_PFB_CASE(7) P25_PFB_CASE(8) P25_PFB_CASE(9) P25_PFB_CASE(10) P25_PFB_CASE(11)
                     P25_PFB_CASE(12) P25_PFB_CASE(13) P25_PFB_CASE(14)
-                    default: sum = branch_sum<15>(win[cc], row, adv, nx[cc][0]); break;
+                    default: branch_run<15>(win[cc], adv, nx0, &sm.tab[0][0], &sm.f0[0][tid + NTH * cc], d0[cc], tt, tt_hi, lim); break;
                 }
-                if (adv) {
-                    nx[cc][0] = nx[cc][1];
-                    nx[cc][1] = nx[cc][2];
-                }
-                sm.f0[tt][tid + NTH * cc] = sum;
             }
         }
         // the (at most three) samples each class receives during the NEXT batch: in flight behind the FFT passes
         if (tb + TB < t_last) {
             const int e_now = e_base + M * (tb + TB - 1);          // the windows describe this output time
 #pragma unroll
-            for (int cc = 0; cc < 2; cc++)
+            for (int cc = 0; cc < 2; cc++) {
+                const int l1 = e_now - d0[cc] + N;
+                if (__all_sync(0xffffffffu, l1 >= HTX && l1 + 2 * N < HTX + n_in)) {      // the usual case: all inside the chunk
+                    const float2* src = chunk + (l1 - HTX);
+                    nx[cc][0] = __ldg(src);
+                    nx[cc][1] = __ldg(src + N);
+                    nx[cc][2] = __ldg(src + 2 * N);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 3; i++) nx[cc][i] = load_logical(tail, chunk, n_in, e_now - d0[cc] + N * (i + 1));
+                    for (int i = 0; i < 3; i++) nx[cc][i] = load_logical(tail, chunk, n_in, l1 + N * i);
+                }
+            }
         }
         __syncthreads();
         // ---- pass A: radix 8, stride 1, no twiddles; in place (read, barrier, write skewed)
@@ -430,7 +478,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_ker
             for (int rr = 0; rr < 2; rr++) {
                 const int item = tid + NTH * rr, tt = item / 96, j = item - 96 * tt, k = j & 7;
 #pragma unroll
-                for (int r = 1; r < 8; r++) v[rr][r] = cmul(v[rr][r], sm.twB[8 * k + r]);
+                for (int r = 1; r < 8; r++) v[rr][r] = cmulw(v[rr][r], sm.twB[r][k]);
                 dft8(v[rr]);
                 const int j0 = (j >> 3) * 64 + k;
 #pragma unroll
@@ -450,7 +498,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_ker
             float2 v[12];
             v[0] = sm.f0[tt][skew(j)];
 #pragma unroll
-            for (int r = 1; r < 12; r++) v[r] = cmul(sm.f0[tt][skew(j + 64 * r)], sm.twC[r][j]);
+            for (int r = 1; r < 12; r++) v[r] = cmulw(sm.f0[tt][skew(j + 64 * r)], sm.twC[r][j]);
             dft12(v);
             const unsigned rbase = inc_remote + (unsigned)((((nb & 1) * TB + tt) * (H / 2) + j) * sizeof(float2));
             const unsigned rmbar = mbar_remote + (unsigned)((nb & 1) * sizeof(unsigned long long));
@@ -473,29 +521,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_ker
         }
         float2 dn[TB];
         const bool full = tt_lo == 0 && tt_hi == TB && tb >= t_first;          // the common case: no per-time tests
+        if (full && !p.y) {
 #pragma unroll
-        for (int tt = 0; tt < TB; tt++) {
-            const int t = tb + tt;
-            dn[tt] = make_float2(0.f, 0.f);
-            if (full || (tt >= tt_lo && tt < tt_hi)) {
-                const float2 wo = cmul(wk, go[tt]);
-                const float2 cur[2] = {cadd(ge[tt], wo), csub(ge[tt], wo)};
-                float dd[2];
+            for (int tt = 0; tt < TB; tt++) dn[tt] = combine_disc(ge[tt], go[tt], wk, cprev, pw);
+        } else {
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const float re = cur[h].x * cprev[h].x + cur[h].y * cprev[h].y;
-                    const float im = cur[h].y * cprev[h].x - cur[h].x * cprev[h].y;
-                    dd[h] = atan2_branchfree(im, re) * P25_FM_GAIN;
-                    cprev[h] = cur[h];
-                }
-                dn[tt] = make_float2(dd[0], dd[1]);
-                if (full || t >= t_first) {
-                    pw[0] += cur[0].x * cur[0].x + cur[0].y * cur[0].y;
-                    pw[1] += cur[1].x * cur[1].x + cur[1].y * cur[1].y;
-                    if (p.y) {
-                        float2* yrow = p.y + ((size_t)cap * p.y_rows + t) * N;
-                        yrow[k2] = cur[0];
-                        yrow[k2 + H] = cur[1];
+            for (int tt = 0; tt < TB; tt++) {
+                const int t = tb + tt;
+                dn[tt] = make_float2(0.f, 0.f);
+                if (tt >= tt_lo && tt < tt_hi) {
+                    float pw_t[2] = {0.f, 0.f};
+                    dn[tt] = combine_disc(ge[tt], go[tt], wk, cprev, pw_t);
+                    if (t >= t_first) {
+                        pw[0] += pw_t[0];
+                        pw[1] += pw_t[1];
+                        if (p.y) {
+                            float2* yrow = p.y + ((size_t)cap * p.y_rows + t) * N;
+                            yrow[k2] = cprev[0];
+                            yrow[k2 + H] = cprev[1];
+                        }
                     }
                 }
             }
