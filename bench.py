@@ -92,7 +92,7 @@ class Workload:
         elif name == "cfg3":
             self.streams, self.fs, self.decim, self.fmt, self.scaling = 8 * 1536, 19_200_000, 400, "cf32", "weak"
             self.kind, self.rows_per_stream = "wide", 1536
-            self.kernel = "pfb channelizer (19.2 MS/s -> 1,536 x 48 kS/s)"
+            self.kernel = "pfb::p25_pfbc_kernel (19.2 MS/s -> 1,536 x 48 kS/s baseband rows, one cluster kernel)"
             self.desc = ("configs[2]: 8 wideband 19.2 MS/s cf32 captures per GPU, 64 of the 1,536 12.5 kHz slots of each carrying a "
                          "control channel, 150 ms per step: polyphase channelizer, every channel demodulated and decoded")
         else:
