@@ -36,6 +36,15 @@ __constant__ float c_sync_fp[P25_FP_LEN];
 #define SEARCH_N 128                          // candidate positions per search step (4 per lane)
 #define WIN_LEN (P25_FP_LEN - 1 + SEARCH_N)  // samples needed to correlate them
 #define WIN_PAD 364                           // staged window, padded to whole 16-byte groups past the last LDS.128
+#define FPP_LEN 248                           // 8 + 240: fingerprint operand of the tensor-pipe prefilter
+// A search step may be skipped when no position can reach the detector's threshold corr > 0 && corr^2 >= rho^2 |fp|^2 en.
+// The prefilter evaluates the same two sums in TF32 on the tensor pipe: inputs truncated to 10 mantissa bits perturb the
+// normalised correlation by less than 2^-9 (Cauchy-Schwarz on the rounding terms), the energy by 2^-10 relative, so a
+// threshold at (rho - 0.01)^2 instead of rho^2 can only err towards running the exact correlator.
+#ifndef P25_PREFILTER_QUIET
+#define P25_PREFILTER_QUIET 2                 // empty search steps in a row before the prefilter is consulted
+#endif
+#define P25_PREFILTER_RHO2_EFP (P25_SYNC_RHO2_EFP * (0.64f * 0.64f) / (0.65f * 0.65f))
 
 struct PendingEvent {
     unsigned kind, len, valid, pad;
@@ -51,6 +60,7 @@ struct WalkShared {
     unsigned surv[P25CU_WALK_WARPS][52];        // 3/4-rate trellis survivors: 8 states x 3 bits per step
     unsigned short pn_a[116], pn_c[116];        // IMBE PN generator n steps ahead: p_n = pn_a[n] * p_0 + pn_c[n] (mod 2^16)
     unsigned char imbe_src[8 * 24];             // inverse of the IMBE interleave schedule: [code word][bit] -> frame bit
+    float fpp[FPP_LEN];                         // sync fingerprint with 8 zeros in front and zeros behind (sync_prefilter)
 };
 
 // packed pair of IEEE fused multiply-adds (one FFMA2): each half is exactly fmaf()
@@ -65,6 +75,43 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
 static_assert(sizeof(P25DevTables) % 16 == 0, "tables are staged with 16-byte copies");
 // pull the cache lines the next step will read into L1 (the row stays in L2 after the demod kernel wrote it)
 __device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Conservative test of one 128-position search step (see P25_PREFILTER_RHO2_EFP): can ANY position be above the
+// detector's threshold?  The 128 correlations are one 16 x 8 tile of the Hankel product
+//     corr[8 a + b] = sum_j win[8 a + j] * fp[j - b],   j = 0 .. 239 (fp = 0 outside 0 .. 230),
+// thirty m16n8k8 steps whose A fragments are plain shared-memory loads of the staged window (rows overlap: no copy of
+// the operand is built) and whose B fragments come from the zero-padded fingerprint; the window energies are the same
+// product with A squared and a band of ones.  31 x fewer math-pipe instructions than the exact FFMA2 correlator, which
+// then only runs on steps that hold a real candidate.  Warp-uniform result.
+__device__ __noinline__ bool sync_prefilter(const float* __restrict__ win, const float* __restrict__ fpp, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const float* wa = win + 8 * g + t;            // A[g][t] of step 0; A[g + 8][.] is 64 samples on
+    const float* fb = fpp + 8 + t - g;            // B[t][g] of step 0: fp[t - g]
+    float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
+    const unsigned one = __float_as_uint(1.0f);
+#pragma unroll 3
+    for (int s = 0; s < 30; s++) {
+        const float x0 = wa[8 * s], x1 = wa[8 * s + 64], x2 = wa[8 * s + 4], x3 = wa[8 * s + 68];
+        const unsigned a[4] = {__float_as_uint(x0), __float_as_uint(x1), __float_as_uint(x2), __float_as_uint(x3)};
+        const unsigned a2[4] = {__float_as_uint(x0 * x0), __float_as_uint(x1 * x1), __float_as_uint(x2 * x2), __float_as_uint(x3 * x3)};
+        mma_tf32(c, a, __float_as_uint(fb[8 * s]), __float_as_uint(fb[8 * s + 4]));
+        // band of ones: 0 <= j - b < 231 with j = 8 s + t (+ 4), b = g -- all ones except in the first and the last two steps
+        const int j0 = 8 * s + t - g;
+        const unsigned o0 = (s >= 1 && s <= 27) ? one : ((j0 >= 0 && j0 < P25_FP_LEN) ? one : 0u);
+        const unsigned o1 = (s >= 1 && s <= 27) ? one : ((j0 + 4 >= 0 && j0 + 4 < P25_FP_LEN) ? one : 0u);
+        mma_tf32(e, a2, o0, o1);
+    }
+    bool hit = false;
+#pragma unroll
+    for (int h = 0; h < 4; h++) hit |= c[h] > 0.f && c[h] * c[h] >= P25_PREFILTER_RHO2_EFP * e[h];
+    return __any_sync(FULL, hit);
+}
 
 struct WarpCtx {
     const WalkParams* p;
@@ -739,7 +786,12 @@ __device__ __forceinline__ void walk_shared_init(WalkShared& sh, const P25DevTab
         }
     }
     for (unsigned i = threadIdx.x; i < 144; i += blockDim.x) sh.imbe_src[tables->imbe_cw[i] * 24 + tables->imbe_bit[i]] = (unsigned char)i;
+    for (int i = threadIdx.x; i < FPP_LEN; i += blockDim.x) sh.fpp[i] = (i >= 8 && i < 8 + P25_FP_LEN) ? c_sync_fp[i - 8] : 0.f;
 }
+// PRE: consult the tensor-pipe prefilter before the exact correlator (contexts whose streams are mostly idle: the
+// channelizer's 1,536 slots per capture).  Decoded output is identical either way; where every stream carries a signal
+// the extra code in the search loop only costs (cfg5: +6 % walker time, A/B in profiles/r02_walk_prefilter_ab.txt).
+template <bool PRE>
 __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(const WalkParams p) {
     __shared__ WalkShared sh;
     walk_shared_init(sh, p.tables);
@@ -808,6 +860,21 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
             }
             if (lane < 5 && wbase + WIN_LEN + 32 * lane < wlim) prefetch_l1(row + wbase + WIN_LEN + 32 * lane);   // next step's new samples
             __syncwarp();
+            // A stream that has just left a frame finds the next sync within a step or two: the prefilter only pays once the
+            // search has come up empty twice (idle and noise-only channels then never run the exact correlator again)
+            if (PRE && ws.quiet >= P25_PREFILTER_QUIET && !sync_prefilter(win, sh.fpp, lane)) {
+                // no position of this step can be above threshold: the detector's carried state is "previous not above"
+                // (prev_corr is only ever compared when the previous position was above)
+                const unsigned long long left0 = end - pos;
+                __syncwarp();
+                if (lane == 0) {
+                    ws.prev_above = 0;
+                    ws.have_prev = 1;
+                    ws.pos = pos + (left0 < SEARCH_N ? left0 : SEARCH_N);
+                }
+                __syncwarp();
+                continue;
+            }
             float2 c01 = make_float2(0.f, 0.f), c23 = c01, e01 = c01, e23 = c01;   // positions h = 0,1 | 2,3
             {
                 const float4* wa = reinterpret_cast<const float4*>(win) + lane;    // wa[m] = win[4 (lane + m) ..]
@@ -876,6 +943,7 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
                 pa = ws.prev_above;
                 hp = ws.have_prev;
             }
+            const bool any_above = PRE && __any_sync(FULL, ab[0] || ab[1] || ab[2] || ab[3]);
             unsigned cand = 0xFFFFFFFFu;
 #pragma unroll
             for (int h = 0; h < 4; h++) {
@@ -899,6 +967,7 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
                     ws.prev_above = la;
                     ws.have_prev = 1;
                     ws.pos = pos + nvalid;
+                    if (PRE) ws.quiet = any_above ? 0 : (ws.quiet < 255 ? ws.quiet + 1 : 255);
                 }
                 __syncwarp();
                 continue;
@@ -930,6 +999,7 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
                 ws.frame_pos = P25_FS_DIBITS;
                 ws.state = WS_NID;
                 ws.cnt = 0;
+                if (PRE) ws.quiet = 0;
             }
             __syncwarp();
             continue;
@@ -1053,7 +1123,7 @@ cudaError_t p25cu_walk_upload_consts() {
     return cudaMemcpyToSymbol(c_sync_fp, P25_SYNC_FP, sizeof(float) * P25_FP_LEN);
 }
 
-cudaError_t p25cu_launch_walk(const WalkParams& p, cudaStream_t st, unsigned max_blocks, int device) {
+cudaError_t p25cu_launch_walk(const WalkParams& p, cudaStream_t st, unsigned max_blocks, int device, bool prefilter) {
     // Beside a demod kernel (max_blocks != 0) keep the SM's shared-memory carve-out at its maximum: that kernel needs
     // ~204 KB per SM and an SM cannot change its carve-out while any CTA is resident on it -- a walker CTA that asked
     // for the default (L1-heavy) split kept the demod CTAs off its SM until it exited (measured: 0.48 -> 0.71 ms).
@@ -1062,23 +1132,27 @@ cudaError_t p25cu_launch_walk(const WalkParams& p, cudaStream_t st, unsigned max
     // device with different overlap settings) may launch from different host threads: the last value set is tracked
     // per device and the set + launch pair runs under a mutex.
     static std::mutex mu;
-    static int carve_state[P25CU_MAX_DEVICES];
+    static int carve_state[2][P25CU_MAX_DEVICES];
     static bool init = false;
     std::lock_guard<std::mutex> lk(mu);
     if (!init) {
-        for (int i = 0; i < P25CU_MAX_DEVICES; i++) carve_state[i] = -2;
+        for (int i = 0; i < P25CU_MAX_DEVICES; i++) carve_state[0][i] = carve_state[1][i] = -2;
         init = true;
     }
     const int want = max_blocks ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
     if (device < 0 || device >= P25CU_MAX_DEVICES) return cudaErrorInvalidDevice;
-    if (carve_state[device] != want) {
-        cudaError_t e = cudaFuncSetAttribute(p25_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, want);
+    if (carve_state[prefilter][device] != want) {
+        cudaError_t e = prefilter ? cudaFuncSetAttribute(p25_walk_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, want)
+                                  : cudaFuncSetAttribute(p25_walk_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, want);
         if (e != cudaSuccess) return e;
-        carve_state[device] = want;
+        carve_state[prefilter][device] = want;
     }
     unsigned blocks = (p.n_streams + P25CU_WALK_WARPS - 1) / P25CU_WALK_WARPS;
     if (max_blocks && blocks > max_blocks) blocks = max_blocks;   // persistent: one small CTA per SM, streams in several passes
-    p25_walk_kernel<<<blocks, 32 * P25CU_WALK_WARPS, 0, st>>>(p);
+    if (prefilter)
+        p25_walk_kernel<true><<<blocks, 32 * P25CU_WALK_WARPS, 0, st>>>(p);
+    else
+        p25_walk_kernel<false><<<blocks, 32 * P25CU_WALK_WARPS, 0, st>>>(p);
     return cudaGetLastError();
 }
 

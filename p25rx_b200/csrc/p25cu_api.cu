@@ -40,6 +40,7 @@ struct p25cu_ctx {
     cudaEvent_t ev_bb_ready[2], ev_bb_free[2];
     cudaEvent_t ev_iq_ready[2], ev_iq_free[2];
     int overlap;               // walker of chunk k runs concurrently with ddc_fm of chunk k+1
+    int walk_prefilter;        // walker consults the tensor-pipe sync prefilter (mostly idle streams: channelizer contexts)
     char err[512];
     unsigned ht;               // input tail length (samples)
     size_t max_out;            // max baseband samples per stream per chunk
@@ -199,6 +200,8 @@ static int create_impl(p25cu_ctx* ctx) {
     // are free); the u8 /50, /5 and channelizer kernels are issue-bound themselves and co-running only slows both (measured).
     ctx->overlap = (cfg.decimation == 50 && cfg.format == P25CU_FMT_CF32_IQ) ? 1 : 0;
     if (const char* e = getenv("P25CU_OVERLAP")) ctx->overlap = atoi(e) ? 1 : 0;   // A/B switch
+    ctx->walk_prefilter = cfg.decimation == (int)p25cu_pfb_decimation() ? 1 : 0;
+    if (const char* e = getenv("P25CU_WALK_PREFILTER")) ctx->walk_prefilter = atoi(e) ? 1 : 0;   // A/B switch (same output either way)
     const size_t S = cfg.n_streams;
     const bool wide = cfg.decimation == (int)p25cu_pfb_decimation();
     ctx->n_captures = wide ? cfg.n_streams / p25cu_pfb_channels() : 0;
@@ -445,7 +448,7 @@ extern "C" int p25cu_decode(p25cu_ctx* ctx, const float* baseband, size_t n) {
     // left (a third would keep a demod CTA from becoming resident: measured 0.51 vs 0.57 ms per step), so the walker
     // is launched as a persistent grid of 2 CTAs per SM that walks the streams in several passes.
     static const int persist = getenv("P25CU_WALK_PERSIST") ? atoi(getenv("P25CU_WALK_PERSIST")) : 2;
-    CK(p25cu_launch_walk(w, ws, ctx->overlap && persist ? (unsigned)(ctx->n_sm * persist) : 0u, ctx->cfg.device));
+    CK(p25cu_launch_walk(w, ws, ctx->overlap && persist ? (unsigned)(ctx->n_sm * persist) : 0u, ctx->cfg.device, ctx->walk_prefilter != 0));
     CK(cudaEventRecord(ctx->ev_bb_free[buf], ws));
     if (!ctx->overlap) CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_bb_free[buf], 0));   // keep stream2 consumers ordered
     ctx->launches++;

@@ -39,7 +39,8 @@ struct __align__(16) WalkHeader {
     unsigned overflow;
     unsigned resync_req;          // set by p25cu_resync, honoured at the next chunk
     unsigned char hex[40];        // hexbits of the link control / crypto sync word being collected
-    unsigned char pad_[4];
+    unsigned char quiet;          // search steps in a row that held no position above threshold (saturates; walker-internal)
+    unsigned char pad_[3];
 };
 static_assert(sizeof(WalkHeader) == 128, "WalkHeader is 8 x 16 bytes");
 
@@ -116,7 +117,7 @@ cudaError_t p25cu_ddc_upload_taps();
 unsigned p25cu_ddc_tail_len(int decimation);
 cudaError_t p25cu_ddc_plan_device(P25DevPlan* plan);   // per-device attribute setup + occupancy (current device)
 cudaError_t p25cu_pfb_plan_device(P25DevPlan* plan);
-cudaError_t p25cu_launch_walk(const WalkParams& p, cudaStream_t st, unsigned max_blocks, int device);
+cudaError_t p25cu_launch_walk(const WalkParams& p, cudaStream_t st, unsigned max_blocks, int device, bool prefilter);
 // Event compaction.  offsets: [2 S + 4] = exclusive event offsets | exclusive word offsets | total events, total words,
 // overflow flag, truncated flag.  mode 0: count only; 1: expand into 80-byte records at dense80; 2: copy the packed
 // words to `packed` (device or mapped host memory, at most cap_words; streams that do not fit stay queued) and mirror

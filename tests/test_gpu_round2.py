@@ -388,3 +388,38 @@ def test_contexts_on_two_devices_in_one_process(p25, oracle):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
     _two_context_case(p25, oracle, [1, 0, 1, 0])
+
+
+# ------------------------------------------------------------------ walker: tensor-pipe sync prefilter
+def test_sync_prefilter_never_changes_the_decoded_output(p25, oracle, monkeypatch):
+    """The TF32 prefilter of the sync search (decode_walk.cu sync_prefilter) may only skip search steps that hold no
+    position above the detector's threshold.  Streams at 3..20 dB (many near-threshold correlations), gaps of silence
+    and pure noise, odd chunk sizes: events, sample indices and stats with the prefilter forced on equal those with it
+    off and the oracle's."""
+    S_ = 40
+    rows = []
+    rng = np.random.default_rng(11)
+    for s in range(S_):
+        if s % 5 == 4:
+            bb = (0.8 * rng.standard_normal(40000)).astype(np.float32)                     # nothing but noise
+        else:
+            st = tx.control_channel(6000 + s, 3, lead_idle=5 * s) if s % 2 else tx.traffic_channel(6000 + s, 1, lead_idle=3 * s)
+            bb = tx.baseband_48k(st.dibits, snr_db=[3, 4, 5, 6, 8, 20][s % 6], seed=s, dc=0.02 * (s % 4), timing_offset=0.3 * (s % 7))[0]
+            if s % 3 == 0:
+                bb = np.concatenate([np.zeros(1500 + 77 * s, np.float32), bb])             # silence first: energy 0 windows
+        rows.append(bb)
+    n = min(len(r) for r in rows)
+    bb = np.stack([r[:n] for r in rows])
+    ref, ref_stats = oracle_events(oracle, bb)
+    got = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("P25CU_WALK_PREFILTER", flag)
+        ctx = p25.Context(S_, max_chunk_samples=1024, max_baseband=5003)
+        rx = p25.MessageReceiver(ctx)
+        ev = np.concatenate([rx.feed(bb[:, i:i + 5003]) for i in range(0, n, 5003)])
+        got[flag] = (ev[np.lexsort((ev["sample"], ev["stream"]))], np.stack([ctx.stats(s) for s in range(S_)]))
+        ctx.close()
+    assert len(ref) > 200
+    for flag in ("1", "0"):
+        assert events_key(got[flag][0]) == events_key(ref), flag
+        assert (got[flag][1] == np.stack(ref_stats)).all(), flag
