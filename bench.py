@@ -14,8 +14,9 @@ and phase-continuous, so consecutive steps are a continuous transmission and eve
              stream) of K x p25cu_process plus one final packed event drain.
   sustained  the same metric over a >= 2 s loop in the production call pattern: every step p25cu_process +
              p25cu_poll_start, events of step k-1 collected (p25cu_poll_packed) while step k runs.
-  e2e        the same metric through the public call sequence with HOST (pinned) input: each step =
-             p25cu_process(host pointer) [H2D copy inside] + p25cu_poll_packed [events written to pinned host memory];
+  e2e        the same metric through the public call sequence with HOST (pinned) input, in the streaming pattern: each
+             step = p25cu_process(host pointer) [H2D copy inside] + p25cu_poll_start, the events of step k-1 collected
+             with p25cu_poll_packed [written to pinned host memory] while step k's copy and kernels run;
              frac_of_h2d_ceiling relates its input bytes/s to a plain pinned cudaMemcpyAsync measured in the same run
              on all ranks at once.
   roofline   dominant kernel of the workload: algorithmic bytes per launch / its own CUDA-event time inside the timed
@@ -541,10 +542,17 @@ def measure(wl: Workload, rank: int, local: int, K: int, W: int, barrier, gate_o
     barrier()
     with torch.cuda.stream(stream):
         e0.record(stream)
+        # the streaming pattern of the sustained leg: step k's H2D copy and kernels are queued before the events of step
+        # k - 1 are collected, so the copy of one step overlaps the kernels of the previous one (two staging buffers on
+        # the library's copy stream); every step's input copy and event drain still lie inside the timed region
         for k in range(Ke):
             ctx.process(host, n)                         # H2D copy of the step's input happens inside
-            w, ne, _ = ctx.poll_packed(copy=False)       # the step's events, written to pinned host memory by the pack kernel
-            d2h += 4 * len(w) + 16
+            ctx.poll_start()                             # pack kernel -> pinned host memory, asynchronous
+            if k:
+                w, ne, _ = ctx.poll_packed(copy=False)   # events of step k - 1
+                d2h += 4 * len(w) + 16
+        w, ne, _ = ctx.poll_packed(copy=False)           # ... and of the last step (synchronises)
+        d2h += 4 * len(w) + 16
         e1.record(stream)
     barrier()
     out["e2e_ms"] = e0.elapsed_time(e1)
