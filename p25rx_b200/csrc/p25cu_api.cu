@@ -74,6 +74,7 @@ struct p25cu_ctx {
     unsigned* h_ring[2];
     unsigned* h_tot[2];        // 4 words each: events, words, overflow, truncated
     cudaEvent_t ev_poll[2];
+    int poll_fence;            // slot + 1 of a started poll whose compaction the next walker on ctx->stream has not been ordered behind yet
     size_t ring_cap_words;
     int ring_head, ring_pending;
     unsigned long long a_abs;  // input samples consumed per stream
@@ -430,6 +431,13 @@ extern "C" int p25cu_decode(p25cu_ctx* ctx, const float* baseband, size_t n) {
     ctx->undecoded = 0;
     cudaStream_t ws = ctx->overlap ? ctx->stream2 : ctx->stream;
     CK(cudaStreamWaitEvent(ws, ctx->ev_bb_ready[buf], 0));
+    if (ctx->poll_fence) {
+        // an asynchronous poll (p25cu_poll_start) compacts on stream2 and resets the streams' event counters there: a walker
+        // on the other stream must not load those counters before it has finished (found by compute-sanitizer's timing:
+        // events of chunk k delivered twice)
+        if (ws != ctx->stream2) CK(cudaStreamWaitEvent(ws, ctx->ev_poll[ctx->poll_fence - 1], 0));
+        ctx->poll_fence = 0;
+    }
     WalkParams w;
     memset(&w, 0, sizeof w);
     w.bb = ctx->d_bb[buf];
@@ -580,6 +588,7 @@ extern "C" int p25cu_poll_start(p25cu_ctx* ctx) {
                             d_tot, ctx->stream2));
     ctx->launches += 2;
     CK(cudaEventRecord(ctx->ev_poll[slot], ctx->stream2));
+    ctx->poll_fence = slot + 1;
     ctx->ring_pending++;
     return P25CU_OK;
 }
