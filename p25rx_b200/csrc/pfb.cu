@@ -106,6 +106,45 @@ __device__ __forceinline__ float atan2_branchfree(float y, float x) {   // same 
     return copysignf(r, y);
 }
 
+__device__ __forceinline__ float2 pk_mul(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&r);
+}
+// atan2_branchfree for two independent arguments at once (two consecutive output times of the thread's channel): the
+// polynomial runs on the packed pipe
+__device__ __forceinline__ float2 atan2x2(float2 y, float2 x) {
+    const float2 mx = make_float2(fmaxf(fabsf(x.x), fabsf(y.x)), fmaxf(fabsf(x.y), fabsf(y.y)));
+    const float2 mn = make_float2(fminf(fabsf(x.x), fabsf(y.x)), fminf(fabsf(x.y), fabsf(y.y)));
+    float2 rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc.x) : "f"(fmaxf(mx.x, 1e-30f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc.y) : "f"(fmaxf(mx.y, 1e-30f)));
+    const float2 t = pk_mul(mn, rc), u = pk_mul(t, t);
+#define P25_C2(c) make_float2(c, c)
+    float2 q = pk_fma(P25_C2(-0.004295386839658022f), u, P25_C2(0.022737378254532814f));
+    q = pk_fma(q, u, P25_C2(-0.057179518043994904f));
+    q = pk_fma(q, u, P25_C2(0.09735459089279175f));
+    q = pk_fma(q, u, P25_C2(-0.13945257663726807f));
+    q = pk_fma(q, u, P25_C2(0.1995391547679901f));
+    q = pk_fma(q, u, P25_C2(-0.3333050608634949f));
+    q = pk_fma(q, u, P25_C2(0.9999995231628418f));
+#undef P25_C2
+    float2 r = pk_mul(q, t);
+    r.x = fabsf(y.x) > fabsf(x.x) ? 1.57079632679489662f - r.x : r.x;
+    r.y = fabsf(y.y) > fabsf(x.y) ? 1.57079632679489662f - r.y : r.y;
+    r.x = x.x < 0.f ? 3.14159265358979324f - r.x : r.x;
+    r.y = x.y < 0.f ? 3.14159265358979324f - r.y : r.y;
+    return make_float2(copysignf(r.x, y.x), copysignf(r.y, y.y));
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 // Round 2 folds the per-channel channel-select FIR (41 taps at 48 kS/s, src/demod.rs:93) into the prototype.  Channel k
 // after the channel filter is
@@ -119,7 +158,7 @@ __device__ __forceinline__ float atan2_branchfree(float y, float x) {   // same 
 // 192 KB ring (8 bytes per MAC, one CTA per SM, no room left to batch the FFT).  This one turns it round:
 //
 //   * CLASS-STATIONARY WINDOWS IN REGISTERS.  The samples that feed FFT input q are exactly those with index
-//     s = -q (mod N): a thread owns two such residue classes and keeps the newest 16 samples of each in registers as a
+//     s = -q (mod N): a thread owns one such residue class and keeps its newest 16 samples in registers as a
 //     circular window.  Per MAC only the 4-byte tap comes from shared memory: the 16 taps that go with a window whose
 //     newest sample lies d0 = n_m - s_newest inputs back are one table row, tap[k] = heq[d0 + N k] (zero outside
 //     0 .. LE - 1), read with four conflict-free LDS.128.  A class receives a new sample in 400 of every 1,536 output
@@ -134,12 +173,15 @@ __device__ __forceinline__ float atan2_branchfree(float y, float x) {   // same 
 //     partner's half through distributed shared memory; CTA b finishes the channels k' in [384 b, 384 b + 384) and
 //     k' + 768.
 //   * EIGHT OUTPUT TIMES PER PASS.  The 768-point transforms of eight consecutive output times go through the three
-//     Stockham passes 8 x 8 x 12 together (96 / 96 / 64 butterflies per time: 768 / 768 / 512 per batch for 384
-//     threads), five CTA barriers and one cluster barrier per eight output times instead of six per time.
-//   * EVERYTHING AFTER THE FFT IS THREAD-LOCAL.  The combine step leaves thread k' with the same two channels at every
-//     output time: c[m-1] for the FM discriminator (src/demod.rs:109-111), the nine older discriminator values of the
-//     10-tap boxcar (src/demod.rs:114) and the power sum (src/demod.rs:95-101) stay in its registers, and it writes
-//     eight consecutive baseband samples of each channel (32 bytes) straight into the walker's rows.
+//     Stockham passes 8 x 8 x 12 together (96 / 96 / 64 butterflies per time: 768 / 768 / 512 per batch for 768
+//     threads), six CTA barriers per eight output times instead of six per time.  The half of the result the partner
+//     needs is stored straight into the partner's shared memory (st.async counting bytes on the partner's mbarrier,
+//     two buffers deep), and the branch sums of the NEXT batch are computed before the combine step waits for it.
+//   * EVERYTHING AFTER THE FFT IS THREAD-LOCAL.  The combine step leaves every thread with the same channel at every
+//     output time: c[m-1] for the FM discriminator (src/demod.rs:109-111) and the power sum (src/demod.rs:95-101)
+//     stay in its registers, the nine older discriminator values of the 10-tap boxcar (src/demod.rs:114) in its own
+//     column of shared memory, and it writes eight consecutive baseband samples of its channel (32 bytes) straight
+//     into the walker's rows.
 //   * A run starts with 10 warm-up output times (c[m-1] and nine discriminator values), recomputed from the carried
 //     input tail instead of carrying discriminator rows between chunks.
 // The index arithmetic is restated thread for thread in spec/pfb_dataflow.py and checked against the float64 oracle on
@@ -147,7 +189,7 @@ __device__ __forceinline__ float atan2_branchfree(float y, float x) {   // same 
 constexpr int PE = 15;                 // taps per branch of the equivalent prototype
 constexpr int LE = N * PE;             // 23,040
 constexpr int H = N / 2;               // FFT length per parity / CTA
-constexpr int NTH = 384;               // threads per CTA: two classes each
+constexpr int NTH = 768;               // threads per CTA: one class and one channel each (24 warps: the phases are latency-bound)
 constexpr int TB = 8;                  // output times per batch
 constexpr int WARM = 10;               // warm-up output times of a run
 constexpr int WS = 16;                 // window slots per class: 15 taps + one sample that may be early
@@ -163,6 +205,7 @@ struct SmemC {
     float2 f0[TB][FSK];                // polyphase sums -> passes A and B in place
     float2 own[TB][H / 2];             // this CTA's transform at the 384 k' it combines itself
     float2 inc[2][TB][H / 2];          // the partner's transform at the same k', written by the partner (st.async), two batches deep
+    float hist[P25_BOXCAR - 1][H];     // the nine discriminator values before the current batch, per channel of this CTA
     unsigned long long mbar[2];        // one transaction barrier per incoming buffer
     float4 twB[8][8];                  // w = exp(+2 pi i k r / 64) at [r][k], as {w, i w} (cmulw)
     float4 twC[12][64];                // w = exp(+2 pi i j r / 768) at [r][j]
@@ -251,45 +294,6 @@ __device__ __forceinline__ void dft12(float2 (&v)[12]) {
     }
 }
 
-// ten-term boxcar over d[i .. i + 9], i = 0..7, d = nine carried values ++ eight new, for the thread's two channels at
-// once (x = channel k', y = channel k' + 768): a tree of pair sums on the packed pipe
-__device__ __forceinline__ void boxcar8(const float2 (&hist)[9], const float2 (&dn)[TB], float2 (&out)[TB]) {
-    float2 d[17];
-#pragma unroll
-    for (int i = 0; i < 9; i++) d[i] = hist[i];
-#pragma unroll
-    for (int i = 0; i < TB; i++) d[9 + i] = dn[i];
-    float2 s2[16], s4[14], s8[8];
-#pragma unroll
-    for (int i = 0; i < 16; i++) s2[i] = cadd(d[i], d[i + 1]);
-#pragma unroll
-    for (int i = 0; i < 14; i++) s4[i] = cadd(s2[i], s2[i + 2]);
-#pragma unroll
-    for (int i = 0; i < 8; i++) s8[i] = cadd(s4[i], s4[i + 4]);
-#pragma unroll
-    for (int i = 0; i < TB; i++) {
-        const float2 t = cadd(s8[i], s2[i + 8]);
-        out[i] = make_float2(t.x * (1.0f / P25_BOXCAR), t.y * (1.0f / P25_BOXCAR));
-    }
-}
-
-// Radix-2 combine of one output time (channels k' and k' + 768 from E[k'], O[k'], w^k'), FM discriminator against the
-// previous output time (src/demod.rs:109-111) and power (src/demod.rs:95-101); cprev is left at this time's spectra.
-__device__ __forceinline__ float2 combine_disc(float2 e, float2 o, float4 wk, float2 (&cprev)[2], float (&pw)[2]) {
-    const float2 wo = cmulw(o, wk);
-    const float2 cur[2] = {cadd(e, wo), csub(e, wo)};
-    float dd[2];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const float re = cur[h].x * cprev[h].x + cur[h].y * cprev[h].y;
-        const float im = cur[h].y * cprev[h].x - cur[h].x * cprev[h].y;
-        dd[h] = atan2_branchfree(im, re) * P25_FM_GAIN;
-        pw[h] += cur[h].x * cur[h].x + cur[h].y * cur[h].y;
-        cprev[h] = cur[h];
-    }
-    return make_float2(dd[0], dd[1]);
-}
-
 // The output times of one class from this one up to (not including) the next window advance, or the end of the batch:
 // the newest sample stays in slot K, slot j holds the ((K - j) mod 16)-th newest, consecutive times differ only in the
 // tap row (d0 grows by M: M / 2 rows on).  Warp-uniform control flow throughout.
@@ -320,7 +324,7 @@ __device__ __forceinline__ void branch_run(float2 (&win)[WS], bool adv, float2 n
     }
 }
 #define P25_PFB_CASE(k) \
-    case k: branch_run<k>(win[cc], adv, nx0, &sm.tab[0][0], &sm.f0[0][tid + NTH * cc], d0[cc], tt, tt_hi, lim); break;
+    case k: branch_run<k>(win, adv, nx0, &sm.tab[0][0], &sm.f0[0][tid], d0, tt, tt_hi, lim); break;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_kernel(const PfbParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -347,154 +351,128 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_ker
 
     for (int i = tid; i < 4 * ROWS; i += NTH) {
         const int g = i / ROWS, row = i - g * ROWS;
-        const int d0 = 2 * row - EARLY + (1 - b);
+        const int d0r = 2 * row - EARLY + (1 - b);
         float t[4];
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
-            const int idx = d0 + N * (4 * g + kk);
+            const int idx = d0r + N * (4 * g + kk);
             t[kk] = (idx >= 0 && idx < LE) ? __ldg(p.taps + idx) : 0.f;
         }
         sm.tab[g][row] = make_float4(t[0], t[1], t[2], t[3]);
     }
     if (tid < 64) sm.twB[tid >> 3][tid & 7] = twiddle4(p.twiddle[24 * (tid >> 3) * (tid & 7)]);
     for (int i = tid; i < 12 * 64; i += NTH) sm.twC[i >> 6][i & 63] = twiddle4(p.twiddle[2 * (i >> 6) * (i & 63)]);
-    const int k2 = H / 2 * b + tid;                                // this thread's channels: k2 and k2 + 768
-    const float4 wk = twiddle4(p.twiddle[k2]);
+#pragma unroll
+    for (int i = 0; i < P25_BOXCAR - 1; i++) sm.hist[i][tid] = 0.f;
+    // this thread's channel: k' = 384 b + kq (the 384 radix-2 pairs this CTA combines), channel k' or k' + 768
+    const int kq = tid < H / 2 ? tid : tid - H / 2;
+    const bool upper = tid >= H / 2;                               // warp-uniform: 384 = 12 warps
+    const int chan = H / 2 * b + kq + (upper ? H : 0);
 
-    // ---- window state of the two classes, describing output time t_first - WARM - 1
+    // ---- window state of the thread's class, describing output time t_first - WARM - 1
     // logical index (tail ++ chunk, tail = HTX samples) of n_m for t = 0; every index below fits 32 bits (n <= 2^30)
     const int e_base = (int)((long long)M * (long long)p.m0 + (M - 1) - (long long)p.a0) + HTX;
-    float2 win[2][WS], nx[2][3];
-    int d0[2], phi[2];
-    const int lim = N - M - 2 * (31 - lane);                       // the warp's last lane reaches d0 >= N at the next output time
+    float2 win[WS], nx[3];
+    int d0, phi = 0;
     {
         const int e_init = e_base + M * (t_first - WARM - 1);
         const int a0m = (int)(p.a0 % (unsigned long long)N);
+        const int c = (N - (2 * tid + b)) % N;                    // residue class of the samples behind FFT input q = 2 tid + b
+        const int cl = (c + HTX % N + N - a0m) % N;               // ... as a residue of the logical index
+        const int rp = (e_init - cl) % N;                         // distance back to the class's latest sample (e_init >= N)
+        const int rp0 = __shfl_sync(0xffffffffu, rp, 0);
+        // lane i sits 2 i inputs below lane 0; if the warp's last lane would already be a whole N behind, the warp
+        // starts one sample ahead (its first lanes then hold an early sample)
+        d0 = rp0 + 2 * lane - (rp0 + 62 >= N ? N : 0);
+        const int lnew = e_init - d0;
 #pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-            const int u = tid + NTH * cc;
-            const int c = (N - (2 * u + b)) % N;                  // residue class of the samples behind FFT input q = 2 u + b
-            const int cl = (c + HTX % N + N - a0m) % N;           // ... as a residue of the logical index
-            const int rp = (e_init - cl) % N;                     // distance back to the class's latest sample (e_init >= N)
-            const int rp0 = __shfl_sync(0xffffffffu, rp, 0);
-            // lane i sits 2 i inputs below lane 0; if the warp's last lane would already be a whole N behind, the warp
-            // starts one sample ahead (its first lanes then hold an early sample)
-            d0[cc] = rp0 + 2 * lane - (rp0 + 62 >= N ? N : 0);
-            phi[cc] = 0;
-            const int lnew = e_init - d0[cc];
+        for (int kk = 0; kk < WS; kk++) win[(WS - kk) & 15] = load_logical(tail, chunk, n_in, lnew - N * kk);
 #pragma unroll
-            for (int kk = 0; kk < WS; kk++) win[cc][(WS - kk) & 15] = load_logical(tail, chunk, n_in, lnew - N * kk);
-        }
+        for (int i = 0; i < 3; i++) nx[i] = load_logical(tail, chunk, n_in, lnew + N * (i + 1));   // arrivals of the first batch
     }
-#pragma unroll
-    for (int cc = 0; cc < 2; cc++)                                 // the samples the classes receive during the first batch
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-            nx[cc][i] = load_logical(tail, chunk, n_in, e_base + M * (t_first - WARM - 1) - d0[cc] + N * (i + 1));
-    float2 cprev[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-    float2 hist[9];                                                // x: channel k2, y: channel k2 + 768
-    float pw[2] = {0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < 9; i++) hist[i] = make_float2(0.f, 0.f);
-    float* const out_lo = p.bb + ((size_t)cap * N + k2) * p.row_stride + P25CU_BB_HIST;
-    float* const out_hi = out_lo + (size_t)H * p.row_stride;
+    float2 cprev = make_float2(0.f, 0.f);
+    float pw = 0.f;
     const int t_begin = t_first - WARM;                            // first output time that is computed
     cluster.sync();                                                // both CTAs' barriers are initialised before either one sends
 
+    // Polyphase branch sums of the (up to eight) output times of the batch that starts at tb_, then the prefetch of the
+    // (at most three) samples the class receives during the batch after it.
+    const auto polyphase = [&](int tb_) {
+        const int tt_lo = max(t_begin - tb_, 0), tt_hi = min(t_last - tb_, TB);      // active output times of that batch
+        const int lim = N - M - 2 * (31 - lane);                   // the warp's last lane reaches d0 >= N at the next output time
+        int tt = tt_lo;
+#pragma unroll 1
+        while (tt < tt_hi) {
+            const bool adv = d0 >= lim;                            // warp-uniform
+            d0 += adv ? M - N : M;
+            const float2 nx0 = nx[0];
+            if (adv) {
+                phi = (phi + 1) & 15;
+                nx[0] = nx[1];
+                nx[1] = nx[2];
+            }
+            switch (phi) {
+                P25_PFB_CASE(0) P25_PFB_CASE(1) P25_PFB_CASE(2) P25_PFB_CASE(3) P25_PFB_CASE(4) P25_PFB_CASE(5)
+                P25_PFB_CASE(6) P25_PFB_CASE(7) P25_PFB_CASE(8) P25_PFB_CASE(9) P25_PFB_CASE(10) P25_PFB_CASE(11)
+                P25_PFB_CASE(12) P25_PFB_CASE(13) P25_PFB_CASE(14)
+                default: branch_run<15>(win, adv, nx0, &sm.tab[0][0], &sm.f0[0][tid], d0, tt, tt_hi, lim); break;
+            }
+        }
+        if (tb_ + TB < t_last) {
+            const int l1 = e_base + M * (tb_ + TB - 1) - d0 + N;   // the window describes output time tb_ + TB - 1
+            if (__all_sync(0xffffffffu, l1 >= HTX && l1 + 2 * N < HTX + n_in)) {      // the usual case: all inside the chunk
+                const float2* src = chunk + (l1 - HTX);
+                nx[0] = __ldg(src);
+                nx[1] = __ldg(src + N);
+                nx[2] = __ldg(src + 2 * N);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 3; i++) nx[i] = load_logical(tail, chunk, n_in, l1 + N * i);
+            }
+        }
+    };
+    // Software pipeline over the batches: the branch sums of batch n + 1 are computed between the last FFT pass of batch n
+    // (which sends half of its result to the partner) and the combine step of batch n (which needs the partner's half),
+    // so the exchange is never waited for (it was 11 % of all warp stalls when the wait followed the send directly).
+    polyphase(t_first - 2 * TB);
     unsigned nb = 0;                                               // batch counter: incoming buffer nb & 1, phase (nb >> 1) & 1
     for (int tb = t_first - 2 * TB; tb < t_last; tb += TB, nb++) {
         if (tid == 0) mbar_expect_tx(smem_u32(&sm.mbar[nb & 1]), INC_BYTES);
-        const int tt_lo = max(t_begin - tb, 0), tt_hi = min(t_last - tb, TB);      // active output times of this batch
-        // ---- polyphase branch sums of up to eight output times, one class after the other
-#pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-            int tt = tt_lo;
-#pragma unroll 1
-            while (tt < tt_hi) {
-                const bool adv = d0[cc] >= lim;                    // warp-uniform
-                d0[cc] += adv ? M - N : M;
-                const float2 nx0 = nx[cc][0];
-                if (adv) {
-                    phi[cc] = (phi[cc] + 1) & 15;
-                    nx[cc][0] = nx[cc][1];
-                    nx[cc][1] = nx[cc][2];
-                }
-                switch (phi[cc]) {
-                    P25_PFB_CASE(0) P25_PFB_CASE(1) P25_PFB_CASE(2) P25_PFB_CASE(3) P25_PFB_CASE(4) P25_PFB_CASE(5)
-                    P25_PFB_CASE(6) P25_PFB_CASE(7) P25_PFB_CASE(8) P25_PFB_CASE(9) P25_PFB_CASE(10) P25_PFB_CASE(11)
-                    P25_PFB_CASE(12) P25_PFB_CASE(13) P25_PFB_CASE(14)
-                    default: branch_run<15>(win[cc], adv, nx0, &sm.tab[0][0], &sm.f0[0][tid + NTH * cc], d0[cc], tt, tt_hi, lim); break;
-                }
-            }
-        }
-        // the (at most three) samples each class receives during the NEXT batch: in flight behind the FFT passes
-        if (tb + TB < t_last) {
-            const int e_now = e_base + M * (tb + TB - 1);          // the windows describe this output time
-#pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
-                const int l1 = e_now - d0[cc] + N;
-                if (__all_sync(0xffffffffu, l1 >= HTX && l1 + 2 * N < HTX + n_in)) {      // the usual case: all inside the chunk
-                    const float2* src = chunk + (l1 - HTX);
-                    nx[cc][0] = __ldg(src);
-                    nx[cc][1] = __ldg(src + N);
-                    nx[cc][2] = __ldg(src + 2 * N);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) nx[cc][i] = load_logical(tail, chunk, n_in, l1 + N * i);
-                }
-            }
-        }
-        __syncthreads();
-        // ---- pass A: radix 8, stride 1, no twiddles; in place (read, barrier, write skewed)
+        const int tt_lo = max(t_begin - tb, 0), tt_hi = min(t_last - tb, TB);        // active output times of this batch
+        __syncthreads();                                           // f0 holds this batch's branch sums
+        // ---- pass A: radix 8, stride 1, no twiddles; in place (read, barrier, write skewed); one butterfly per thread
         {
-            float2 v[2][8];
+            const int tt = tid / 96, j = tid - 96 * tt;
+            float2 v[8];
 #pragma unroll
-            for (int rr = 0; rr < 2; rr++) {
-                const int item = tid + NTH * rr, tt = item / 96, j = item - 96 * tt;
-#pragma unroll
-                for (int r = 0; r < 8; r++) v[rr][r] = sm.f0[tt][j + 96 * r];
-            }
+            for (int r = 0; r < 8; r++) v[r] = sm.f0[tt][j + 96 * r];
             __syncthreads();
+            dft8(v);
 #pragma unroll
-            for (int rr = 0; rr < 2; rr++) {
-                const int item = tid + NTH * rr, tt = item / 96, j = item - 96 * tt;
-                dft8(v[rr]);
-#pragma unroll
-                for (int q = 0; q < 8; q++) sm.f0[tt][skew(8 * j + q)] = v[rr][q];
-            }
+            for (int q = 0; q < 8; q++) sm.f0[tt][skew(8 * j + q)] = v[q];
         }
         __syncthreads();
         // ---- pass B: radix 8, stride 8
         {
-            float2 v[2][8];
+            const int tt = tid / 96, j = tid - 96 * tt, k = j & 7;
+            float2 v[8];
 #pragma unroll
-            for (int rr = 0; rr < 2; rr++) {
-                const int item = tid + NTH * rr, tt = item / 96, j = item - 96 * tt;
-#pragma unroll
-                for (int r = 0; r < 8; r++) v[rr][r] = sm.f0[tt][skew(j + 96 * r)];
-            }
+            for (int r = 0; r < 8; r++) v[r] = sm.f0[tt][skew(j + 96 * r)];
             __syncthreads();
 #pragma unroll
-            for (int rr = 0; rr < 2; rr++) {
-                const int item = tid + NTH * rr, tt = item / 96, j = item - 96 * tt, k = j & 7;
+            for (int r = 1; r < 8; r++) v[r] = cmulw(v[r], sm.twB[r][k]);
+            dft8(v);
+            const int j0 = (j >> 3) * 64 + k;
 #pragma unroll
-                for (int r = 1; r < 8; r++) v[rr][r] = cmulw(v[rr][r], sm.twB[r][k]);
-                dft8(v[rr]);
-                const int j0 = (j >> 3) * 64 + k;
-#pragma unroll
-                for (int q = 0; q < 8; q++) sm.f0[tt][skew(j0 + 8 * q)] = v[rr][q];
-            }
+            for (int q = 0; q < 8; q++) sm.f0[tt][skew(j0 + 8 * q)] = v[q];
         }
         __syncthreads();
-        // ---- pass C: radix 12, stride 64.  Outputs k' = j + 64 q: q < 6 lies in CTA 0's combine range, q >= 6 in CTA 1's;
-        // the half this CTA combines itself stays here, the other goes straight into the partner's incoming buffer.  The
-        // partner cannot still be reading that buffer: it holds the batch before last, and the partner's data of the last
-        // batch -- sent after it had finished with that one -- has already been consumed here.
-#pragma unroll 1
-        for (int rr = 0; rr < 2; rr++) {
-            const int item = tid + NTH * rr;
-            if (item >= TB * 64) break;
-            const int tt = item >> 6, j = item & 63;
+        // ---- pass C: radix 12, stride 64 (512 butterflies).  Outputs k' = j + 64 q: q < 6 lies in CTA 0's combine range,
+        // q >= 6 in CTA 1's; the half this CTA combines itself stays here, the other goes straight into the partner's
+        // incoming buffer.  The partner cannot still be reading that buffer: it holds the batch before last, and the
+        // partner's data of the last batch -- sent after it had finished with that one -- has already been consumed here.
+        if (tid < TB * 64) {
+            const int tt = tid >> 6, j = tid & 63;
             float2 v[12];
             v[0] = sm.f0[tt][skew(j)];
 #pragma unroll
@@ -509,67 +487,81 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_ker
                 st_async_f2(rbase + (unsigned)(64 * q * sizeof(float2)), theirs, rmbar);
             }
         }
-        __syncthreads();                                           // own[] complete
-        mbar_wait(smem_u32(&sm.mbar[nb & 1]), (nb >> 1) & 1);      // ... and all of the partner's half has landed
-        // ---- radix-2 combine across the pair, discriminator, boxcar, baseband rows: two channels per thread
-        float2 ge[TB], go[TB];
+        __syncthreads();                                           // own[] complete, f0 free
+        if (tb + TB < t_last) polyphase(tb + TB);
+        mbar_wait(smem_u32(&sm.mbar[nb & 1]), (nb >> 1) & 1);      // all of the partner's half has landed (long ago)
+        // ---- radix-2 combine across the pair, discriminator, boxcar, baseband row: one channel per thread
+        {
+            const float4 wk = twiddle4(__ldg(p.twiddle + H / 2 * b + kq));
+            const bool full = tt_lo == 0 && tt_hi == TB && tb >= t_first;      // the common case: no per-time tests
+            float dn[TB];
+            if (full && !p.y) {
+                float2 cur[TB];
 #pragma unroll
-        for (int tt = 0; tt < TB; tt++) {
-            const float2 mine = sm.own[tt][tid], theirs = sm.inc[nb & 1][tt][tid];
-            ge[tt] = b == 0 ? mine : theirs;
-            go[tt] = b == 0 ? theirs : mine;
-        }
-        float2 dn[TB];
-        const bool full = tt_lo == 0 && tt_hi == TB && tb >= t_first;          // the common case: no per-time tests
-        if (full && !p.y) {
+                for (int tt = 0; tt < TB; tt++) {
+                    const float2 mine = sm.own[tt][kq], theirs = sm.inc[nb & 1][tt][kq];
+                    const float2 e = b == 0 ? mine : theirs, wo = cmulw(b == 0 ? theirs : mine, wk);
+                    cur[tt] = upper ? csub(e, wo) : cadd(e, wo);
+                    pw += cur[tt].x * cur[tt].x + cur[tt].y * cur[tt].y;
+                }
 #pragma unroll
-            for (int tt = 0; tt < TB; tt++) dn[tt] = combine_disc(ge[tt], go[tt], wk, cprev, pw);
-        } else {
+                for (int tt = 0; tt < TB; tt += 2) {               // two output times per discriminator evaluation
+                    const float2 p0 = tt ? cur[tt - 1] : cprev, c0 = cur[tt], c1 = cur[tt + 1];
+                    const float2 re = make_float2(c0.x * p0.x + c0.y * p0.y, c1.x * c0.x + c1.y * c0.y);
+                    const float2 im = make_float2(c0.y * p0.x - c0.x * p0.y, c1.y * c0.x - c1.x * c0.y);
+                    const float2 th = atan2x2(im, re);
+                    dn[tt] = th.x * P25_FM_GAIN;
+                    dn[tt + 1] = th.y * P25_FM_GAIN;
+                }
+                cprev = cur[TB - 1];
+            } else {
 #pragma unroll
-            for (int tt = 0; tt < TB; tt++) {
-                const int t = tb + tt;
-                dn[tt] = make_float2(0.f, 0.f);
-                if (tt >= tt_lo && tt < tt_hi) {
-                    float pw_t[2] = {0.f, 0.f};
-                    dn[tt] = combine_disc(ge[tt], go[tt], wk, cprev, pw_t);
-                    if (t >= t_first) {
-                        pw[0] += pw_t[0];
-                        pw[1] += pw_t[1];
-                        if (p.y) {
-                            float2* yrow = p.y + ((size_t)cap * p.y_rows + t) * N;
-                            yrow[k2] = cprev[0];
-                            yrow[k2 + H] = cprev[1];
+                for (int tt = 0; tt < TB; tt++) {
+                    float d_t = 0.f;
+                    if (tt >= tt_lo && tt < tt_hi) {
+                        const float2 mine = sm.own[tt][kq], theirs = sm.inc[nb & 1][tt][kq];
+                        const float2 e = b == 0 ? mine : theirs, wo = cmulw(b == 0 ? theirs : mine, wk);
+                        const float2 cur = upper ? csub(e, wo) : cadd(e, wo);
+                        const float re = cur.x * cprev.x + cur.y * cprev.y;
+                        const float im = cur.y * cprev.x - cur.x * cprev.y;
+                        d_t = atan2_branchfree(im, re) * P25_FM_GAIN;
+                        cprev = cur;
+                        if (tb + tt >= t_first) {
+                            pw += cur.x * cur.x + cur.y * cur.y;
+                            if (p.y) p.y[((size_t)cap * p.y_rows + tb + tt) * N + chan] = cur;
                         }
                     }
+                    dn[tt] = d_t;
                 }
             }
-        }
-        {
-            float2 box[TB];
-            boxcar8(hist, dn, box);
-            hist[0] = hist[8];
+            // ten-term boxcar over (nine carried values ++ eight new), a tree of pair sums
+            float d[17];
 #pragma unroll
-            for (int i = 0; i < TB; i++) hist[1 + i] = dn[i];
+            for (int i = 0; i < 9; i++) d[i] = sm.hist[i][tid];
+#pragma unroll
+            for (int i = 0; i < TB; i++) d[9 + i] = dn[i];
+#pragma unroll
+            for (int i = 0; i < 9; i++) sm.hist[i][tid] = d[8 + i];
+            float s2[16], s4[14], box[TB];
+#pragma unroll
+            for (int i = 0; i < 16; i++) s2[i] = d[i] + d[i + 1];
+#pragma unroll
+            for (int i = 0; i < 14; i++) s4[i] = s2[i] + s2[i + 2];
+#pragma unroll
+            for (int i = 0; i < TB; i++) box[i] = ((s4[i] + s4[i + 4]) + s2[i + 8]) * (1.0f / P25_BOXCAR);
+            float* out = p.bb + ((size_t)cap * N + chan) * p.row_stride + P25CU_BB_HIST + tb;
             if (full) {
-                *reinterpret_cast<float4*>(out_lo + tb) = make_float4(box[0].x, box[1].x, box[2].x, box[3].x);
-                *reinterpret_cast<float4*>(out_lo + tb + 4) = make_float4(box[4].x, box[5].x, box[6].x, box[7].x);
-                *reinterpret_cast<float4*>(out_hi + tb) = make_float4(box[0].y, box[1].y, box[2].y, box[3].y);
-                *reinterpret_cast<float4*>(out_hi + tb + 4) = make_float4(box[4].y, box[5].y, box[6].y, box[7].y);
+                *reinterpret_cast<float4*>(out) = make_float4(box[0], box[1], box[2], box[3]);
+                *reinterpret_cast<float4*>(out + 4) = make_float4(box[4], box[5], box[6], box[7]);
             } else {
 #pragma unroll
                 for (int i = 0; i < TB; i++)
-                    if (tb + i >= t_first && tb + i < t_last) {
-                        out_lo[tb + i] = box[i].x;
-                        out_hi[tb + i] = box[i].y;
-                    }
+                    if (tb + i >= t_first && tb + i < t_last) out[i] = box[i];
             }
         }
     }
     cluster.sync();                                                // neither CTA leaves while the other may still send to it
-    if (p.power_sum) {
-        atomicAdd(p.power_sum + (size_t)cap * N + k2, pw[0]);
-        atomicAdd(p.power_sum + (size_t)cap * N + k2 + H, pw[1]);
-    }
+    if (p.power_sum) atomicAdd(p.power_sum + (size_t)cap * N + chan, pw);
 }
 #undef P25_PFB_CASE
 

@@ -2,7 +2,8 @@
 
 Not the oracle (that is oracle/pfb_oracle.py) and not product code: this restates, thread for thread, the index
 arithmetic of the kernel -- class-stationary register windows that advance a warp at a time, the tap rows indexed by
-the distance back to the newest sample (early samples meet a zero tap), the parity split over the two CTAs of a cluster, the 8 x 8 x 12 Stockham passes with the skewed buffer and the radix-2 combine -- so that
+the distance back to the newest sample (early samples meet a zero tap), the parity split over the two CTAs of a
+cluster, the 8 x 8 x 12 Stockham passes with the skewed buffer and the radix-2 combine -- so that
 tests/test_pfb_oracle.py can check the decomposition against the float64 definition on the CPU, before any GPU run.
 
 Definitions (pfb.cu header):  c_k[m] = sum_i heq[i] x[n_m - i] exp(-2j pi k (n_m - i) / N),  n_m = M m + M - 1,
@@ -16,7 +17,7 @@ import numpy as np
 N, M, PE = 1536, 400, 15
 LE = N * PE
 H = N // 2                 # FFT length per parity
-NTH = 384                  # threads per CTA, two classes each
+NTH = 768                  # threads per CTA: one class (FFT input u = tid) and one channel each
 TB = 8                     # output times per batch
 WARM = 10                  # warm-up output times per run (1 for c[m-1], 9 for the boxcar history)
 WS = 16                    # window slots per class
@@ -83,7 +84,7 @@ class Run:
         e_init = e_base + M * t_init
         st = []
         for b in (0, 1):
-            u = np.concatenate([np.arange(NTH), np.arange(NTH) + NTH])  # FFT inputs of thread tid: u = tid, tid + 384
+            u = np.arange(NTH)                                          # FFT input of thread tid: u = tid
             lane = u % 32
             c = (-(2 * u + b)) % N
             cl = (c - a0 + HTX) % N
@@ -115,7 +116,7 @@ class Run:
                 V = np.zeros(H, dtype=self.logical.dtype)
                 for j in range(WS):
                     V += s["slots"][j] * self.tabs[b][row, (s["phi"] - j) % WS]
-                EO.append(idft768(V))                                   # thread order == FFT input order (u = tid, tid + 384)
+                EO.append(idft768(V))                                   # thread order == FFT input order (u = tid)
             E, O = EO
             k = np.arange(H)
             w = np.exp(2j * np.pi * k / N)
