@@ -573,14 +573,17 @@ def h2d_ceiling(local: int, barrier):
     d = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{local}")
     d.copy_(h, non_blocking=True)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(4):
-        d.copy_(h, non_blocking=True)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = None
+    for _ in range(3):                                   # best of three: the ceiling is what the box can deliver
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(4):
+            d.copy_(h, non_blocking=True)
+        e1.record()
+        barrier()
+        t = e0.elapsed_time(e1)
+        ms = t if ms is None else min(ms, t)
     del h, d
     torch.cuda.empty_cache()
     return 4 * nbytes, ms
@@ -681,7 +684,7 @@ def run_b200(args):
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": head["config"], "realtime_channels": head["realtime_channels"], "e2e": head["e2e"],
             "gpu_launches": int(m["launches"]), "kernels": head["kernels"], "roofline": head["roofline"],
-            "clocks": m.get("clocks") or sampler.result(), "h2d_ceiling": {"gbs_all_ranks": h2d_gbs, "how": "4 x 1 GiB pinned cudaMemcpyAsync per rank, all ranks at once, max over ranks"}}
+            "clocks": m.get("clocks") or sampler.result(), "h2d_ceiling": {"gbs_all_ranks": h2d_gbs, "how": "4 x 1 GiB pinned cudaMemcpyAsync per rank, all ranks at once, max over ranks, best of 3"}}
     for k in ("sustained", "oracle_check"):
         if k in head:
             line[k] = head[k]

@@ -423,3 +423,49 @@ def test_sync_prefilter_never_changes_the_decoded_output(p25, oracle, monkeypatc
     for flag in ("1", "0"):
         assert events_key(got[flag][0]) == events_key(ref), flag
         assert (got[flag][1] == np.stack(ref_stats)).all(), flag
+
+
+def test_cfg3_bench_geometry_sampled_against_oracle(p25, oracle):
+    """BASELINE configs[2] as bench.py times it -- 8 wideband captures x 2,880,000 samples through the cluster channelizer
+    kernel (9 runs of 800 output times per capture, each with its own warm-up from the carried tail), two consecutive
+    steps -- 12 sampled (capture, channel) streams against the definition: mix down, 6,144-tap prototype, keep every 400th
+    (scipy upfirdn, float64), then the oracle's 48 kHz chain and receiver.  Occupied channels: baseband within the FP32
+    tolerance; all sampled streams: events identical."""
+    import torch
+    from scipy import signal
+    from bench import Workload
+    wl = Workload("cfg3", 1)
+    n, caps = wl.n, wl.rows
+    dev = wl.device_input(0)
+    ctx = p25.Context(wl.streams, fmt=p25.FMT_CF32_IQ, decimation=400, max_chunk_samples=n, event_slots=64)
+    n_steps, got_ev = 2, []
+    for _ in range(n_steps):
+        ctx.process(dev, n)
+        got_ev.append(ctx.poll())
+    n_out = n // 400
+    ev = np.concatenate(got_ev)
+    h = S.taps_pfb().astype(np.float64)
+    occupied = [(37 * i + 5) % 1536 for i in range(64)]
+    idle = [k for k in range(1536) if k not in occupied]
+    sample = [(c, k) for c in (0, 3, 7) for k in (occupied[0], occupied[31], occupied[63], idle[5 + 100 * c])]
+    oracle.lib().p25o_set_always_correlate(0)
+    nn = np.arange(n_steps * n)
+    ref_ev, worst = [], 0.0
+    for c, k in sample:
+        x = np.tile(wl.oracle_row(c).astype(np.complex128), n_steps)                      # both steps of this capture
+        xm = x * np.exp(-2j * np.pi * ((k * nn) % 1536) / 1536.0)
+        y = signal.upfirdn(h, np.concatenate([[0.0], xm]), up=1, down=400)[1:n_steps * n // 400 + 1]   # newest input 400 m + 399
+        rbb = oracle.DemodChain(oracle.FMT_CF32, 2).feed(y.astype(np.complex64))
+        s_id = c * 1536 + k
+        ref_ev.append(oracle.MessageReceiver(stream=s_id).feed(rbb))
+        if k in occupied:                                                                  # second step: what the device still holds
+            bb = ctx.read_baseband(s_id, n_out)
+            worst = max(worst, float(np.max(np.abs(bb - rbb[n_out:]))))
+    ref_ev = np.concatenate(ref_ev)
+    ref_ev = ref_ev[np.lexsort((ref_ev["sample"], ref_ev["stream"]))]
+    ids = [c * 1536 + k for c, k in sample]
+    got = ev[np.isin(ev["stream"], ids)]
+    got = got[np.lexsort((got["sample"], got["stream"]))]
+    assert worst < BB_TOL, worst
+    assert len(ref_ev) >= 9 * 6 and events_key(got) == events_key(ref_ev)
+    ctx.close()
