@@ -36,15 +36,18 @@ __constant__ float c_sync_fp[P25_FP_LEN];
 #define SEARCH_N 128                          // candidate positions per search step (4 per lane)
 #define WIN_LEN (P25_FP_LEN - 1 + SEARCH_N)  // samples needed to correlate them
 #define WIN_PAD 364                           // staged window, padded to whole 16-byte groups past the last LDS.128
-#define FPP_LEN 248                           // 8 + 240: fingerprint operand of the tensor-pipe prefilter
+#define FPB_LEN 256                           // packed fingerprint pairs, operand of the tensor-pipe prefilter
 // A search step may be skipped when no position can reach the detector's threshold corr > 0 && corr^2 >= rho^2 |fp|^2 en.
-// The prefilter evaluates the same two sums in TF32 on the tensor pipe: inputs truncated to 10 mantissa bits perturb the
-// normalised correlation by less than 2^-9 (Cauchy-Schwarz on the rounding terms), the energy by 2^-10 relative, so a
-// threshold at (rho - 0.01)^2 instead of rho^2 can only err towards running the exact correlator.
+// The prefilter bounds both sides from the safe direction:
+//   * the 128 correlations in BF16 on the tensor pipe: inputs rounded to 8 mantissa bits perturb a product by less than
+//     2^-8 relative, the normalised correlation therefore by less than 2^-8 = 0.004 (Cauchy-Schwarz on the rounding terms);
+//   * the window energy from BELOW: the 27 whole 8-sample blocks that lie inside every window of a row of 8 positions
+//     (216 of the 231 samples), from block energies and one warp prefix sum.
+// Testing corr' > 0 && corr'^2 >= (rho - 0.02)^2 |fp|^2 en_low can therefore only err towards running the exact correlator.
 #ifndef P25_PREFILTER_QUIET
 #define P25_PREFILTER_QUIET 2                 // empty search steps in a row before the prefilter is consulted
 #endif
-#define P25_PREFILTER_RHO2_EFP (P25_SYNC_RHO2_EFP * (0.64f * 0.64f) / (0.65f * 0.65f))
+#define P25_PREFILTER_RHO2_EFP (P25_SYNC_RHO2_EFP * (0.63f * 0.63f) / (0.65f * 0.65f))
 
 struct PendingEvent {
     unsigned kind, len, valid, pad;
@@ -60,7 +63,8 @@ struct WalkShared {
     unsigned surv[P25CU_WALK_WARPS][52];        // 3/4-rate trellis survivors: 8 states x 3 bits per step
     unsigned short pn_a[116], pn_c[116];        // IMBE PN generator n steps ahead: p_n = pn_a[n] * p_0 + pn_c[n] (mod 2^16)
     unsigned char imbe_src[8 * 24];             // inverse of the IMBE interleave schedule: [code word][bit] -> frame bit
-    float fpp[FPP_LEN];                         // sync fingerprint with 8 zeros in front and zeros behind (sync_prefilter)
+    unsigned fpb[FPB_LEN];                      // sync fingerprint as BF16 pairs: fpb[i] = (fp[i - 8], fp[i - 7]), zeros outside (sync_prefilter)
+    float pe[P25CU_WALK_WARPS][48];             // prefix sums of the 8-sample block energies of the staged window
 };
 
 // packed pair of IEEE fused multiply-adds (one FFMA2): each half is exactly fmaf()
@@ -76,45 +80,61 @@ static_assert(sizeof(P25DevTables) % 16 == 0, "tables are staged with 16-byte co
 // pull the cache lines the next step will read into L1 (the row stays in L2 after the demod kernel wrote it)
 __device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// two floats -> one register of two BF16 (round to nearest), lo in bits 0..15
+__device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
+    unsigned r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 
 // Conservative test of one 128-position search step (see P25_PREFILTER_RHO2_EFP): can ANY position be above the
 // detector's threshold?  The 128 correlations are one 16 x 8 tile of the Hankel product
 //     corr[8 a + b] = sum_j win[8 a + j] * fp[j - b],   j = 0 .. 239 (fp = 0 outside 0 .. 230),
-// thirty m16n8k8 steps whose A fragments are plain shared-memory loads of the staged window (rows overlap: no copy of
-// the operand is built) and whose B fragments come from the zero-padded fingerprint; the window energies are the same
-// product with A squared and a band of ones.  31 x fewer math-pipe instructions than the exact FFMA2 correlator, which
-// then only runs on steps that hold a real candidate.  Warp-uniform result.
-// one k-step of the two Hankel products; BAND: the band of ones needs its edges (first and last two steps)
-template <bool BAND>
-__device__ __forceinline__ void prefilter_step(const float* __restrict__ wa, const float* __restrict__ fb, int j0, float (&c)[4], float (&e)[4]) {
-    const float x0 = wa[0], x1 = wa[64], x2 = wa[4], x3 = wa[68];
-    const unsigned a[4] = {__float_as_uint(x0), __float_as_uint(x1), __float_as_uint(x2), __float_as_uint(x3)};
-    const unsigned a2[4] = {__float_as_uint(x0 * x0), __float_as_uint(x1 * x1), __float_as_uint(x2 * x2), __float_as_uint(x3 * x3)};
-    mma_tf32(c, a, __float_as_uint(fb[0]), __float_as_uint(fb[4]));
-    const unsigned one = __float_as_uint(1.0f);
-    // band of ones: 0 <= j - b < 231 with j = 8 s + t (+ 4), b = g
-    const unsigned o0 = !BAND || (j0 >= 0 && j0 < P25_FP_LEN) ? one : 0u;
-    const unsigned o1 = !BAND || (j0 + 4 >= 0 && j0 + 4 < P25_FP_LEN) ? one : 0u;
-    mma_tf32(e, a2, o0, o1);
-}
-__device__ __noinline__ bool sync_prefilter(const float* __restrict__ win, const float* __restrict__ fpp, int lane) {
+// fifteen m16n8k16 steps whose A fragments are 8-byte shared-memory loads of the staged window (rows overlap: no copy of
+// the operand is built; the 32 lanes of a load cover 256 consecutive bytes) and whose B fragments come from a table of
+// packed fingerprint pairs.  15 tensor instructions instead of 924 FFMA2 per lane; the exact correlator then only runs
+// on steps that hold a real candidate.  Warp-uniform result.
+__device__ __noinline__ bool sync_prefilter(const float* __restrict__ win, const unsigned* __restrict__ fpb, float* __restrict__ pe, int lane) {
     const int g = lane >> 2, t = lane & 3;
-    const float* wa = win + 8 * g + t;            // A[g][t] of step 0; A[g + 8][.] is 64 samples on
-    const float* fb = fpp + 8 + t - g;            // B[t][g] of step 0: fp[t - g]
-    float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
-    prefilter_step<true>(wa, fb, t - g, c, e);
-#pragma unroll 9
-    for (int s = 1; s < 28; s++) prefilter_step<false>(wa + 8 * s, fb + 8 * s, 0, c, e);
-    prefilter_step<true>(wa + 8 * 28, fb + 8 * 28, 8 * 28 + t - g, c, e);
-    prefilter_step<true>(wa + 8 * 29, fb + 8 * 29, 8 * 29 + t - g, c, e);
-    bool hit = false;
+    // ---- lower bound of the window energies: blocks of 8 samples, prefix sums, 27 whole blocks per row of positions
+    {
+        const float4* w4 = reinterpret_cast<const float4*>(win);
+        const float4 u0 = w4[2 * lane], u1 = w4[2 * lane + 1];
+        float ea = u0.x * u0.x + u0.y * u0.y + u0.z * u0.z + u0.w * u0.w + u1.x * u1.x + u1.y * u1.y + u1.z * u1.z + u1.w * u1.w, eb = 0.f;
+        if (lane < 13) {                          // blocks 32 .. 44: samples 256 .. 359
+            const float4 v0 = w4[2 * (lane + 32)], v1 = w4[2 * (lane + 32) + 1];
+            eb = v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
+        }
 #pragma unroll
-    for (int h = 0; h < 4; h++) hit |= c[h] > 0.f && c[h] * c[h] >= P25_PREFILTER_RHO2_EFP * e[h];
+        for (int o = 1; o < 32; o <<= 1) {
+            const float xa = __shfl_up_sync(FULL, ea, o), xb = __shfl_up_sync(FULL, eb, o);
+            if (lane >= o) {
+                ea += xa;
+                eb += xb;
+            }
+        }
+        eb += __shfl_sync(FULL, ea, 31);
+        pe[lane] = ea;                            // pe[m] = energy of blocks 0 .. m
+        if (lane < 13) pe[32 + lane] = eb;
+    }
+    const float2* wa = reinterpret_cast<const float2*>(win + 8 * g + 2 * t);   // A[g][2t, 2t+1] of step 0; row g + 8 is 64 samples on
+    const unsigned* fb = fpb + 8 + 2 * t - g;                                     // B[2t, 2t+1][g] of step 0: (fp[2t - g], fp[2t + 1 - g])
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 5
+    for (int s = 0; s < 15; s++) {
+        const float2 x0 = wa[8 * s], x1 = wa[8 * s + 32], x2 = wa[8 * s + 4], x3 = wa[8 * s + 36];
+        const unsigned a[4] = {pack_bf16(x0.x, x0.y), pack_bf16(x1.x, x1.y), pack_bf16(x2.x, x2.y), pack_bf16(x3.x, x3.y)};
+        mma_bf16(c, a, fb[16 * s], fb[16 * s + 8]);
+    }
+    __syncwarp();
+    const float l0 = pe[g + 27] - pe[g], l1 = pe[g + 35] - pe[g + 8];   // blocks a + 1 .. a + 27 lie inside every window of row a
+    const bool hit = (c[0] > 0.f && c[0] * c[0] >= P25_PREFILTER_RHO2_EFP * l0) || (c[1] > 0.f && c[1] * c[1] >= P25_PREFILTER_RHO2_EFP * l0) ||
+                     (c[2] > 0.f && c[2] * c[2] >= P25_PREFILTER_RHO2_EFP * l1) || (c[3] > 0.f && c[3] * c[3] >= P25_PREFILTER_RHO2_EFP * l1);
     return __any_sync(FULL, hit);
 }
 
@@ -791,7 +811,10 @@ __device__ __forceinline__ void walk_shared_init(WalkShared& sh, const P25DevTab
         }
     }
     for (unsigned i = threadIdx.x; i < 144; i += blockDim.x) sh.imbe_src[tables->imbe_cw[i] * 24 + tables->imbe_bit[i]] = (unsigned char)i;
-    for (int i = threadIdx.x; i < FPP_LEN; i += blockDim.x) sh.fpp[i] = (i >= 8 && i < 8 + P25_FP_LEN) ? c_sync_fp[i - 8] : 0.f;
+    for (int i = threadIdx.x; i < FPB_LEN; i += blockDim.x) {
+        const float lo = (i >= 8 && i < 8 + P25_FP_LEN) ? c_sync_fp[i - 8] : 0.f, hi = (i >= 7 && i < 7 + P25_FP_LEN) ? c_sync_fp[i - 7] : 0.f;
+        sh.fpb[i] = pack_bf16(lo, hi);
+    }
 }
 // PRE: consult the tensor-pipe prefilter before the exact correlator (contexts whose streams are mostly idle: the
 // channelizer's 1,536 slots per capture).  Decoded output is identical either way; where every stream carries a signal
@@ -867,8 +890,8 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
             __syncwarp();
             // A stream that has just left a frame finds the next sync within a step or two: the prefilter only pays once the
             // search has come up empty twice (idle and noise-only channels then never run the exact correlator again).
-            // It reads the staged window: fragments straight from the row through L1 measured slower (1.18 vs 1.07 ms).
-            if (PRE && ws.quiet >= P25_PREFILTER_QUIET && !sync_prefilter(win, sh.fpp, lane)) {
+            // It reads the staged window: fragments straight from the row through L1 measured slower.
+            if (PRE && ws.quiet >= P25_PREFILTER_QUIET && !sync_prefilter(win, sh.fpb, sh.pe[warp], lane)) {
                 // no position of this step can be above threshold: the detector's carried state is "previous not above"
                 // (prev_corr is only ever compared when the previous position was above)
                 const unsigned long long left0 = end - pos;
