@@ -1482,6 +1482,10 @@ cudaError_t p25cu_ddc_plan_device(P25DevPlan* plan) {
     if ((e = plan_one(fast5::p25_ddc5_fm_kernel<CF>, fast5::K<CF>::NT, sizeof(fast5::Smem<CF>), n_sm, &plan->grid_fast5[CF])) != cudaSuccess) return e;
     if ((e = plan_one(w5::p25_ddc5_warp_kernel<U8, false>, 32 * w5::WARPS, sizeof(w5::WarpSm<U8>) * w5::WARPS, n_sm, &plan->grid_w5[U8])) != cudaSuccess) return e;
     if ((e = plan_one(w5::p25_ddc5_warp_kernel<CF, false>, 32 * w5::WARPS, sizeof(w5::WarpSm<CF>) * w5::WARPS, n_sm, &plan->grid_w5[CF])) != cudaSuccess) return e;
+    if (const char* ev = getenv("P25CU_W5_CTAS")) {    // A/B: CTAs per SM of the persistent /5 warp-kernel grids
+        const int per_sm = atoi(ev);
+        if (per_sm > 0) plan->grid_w5[U8] = plan->grid_w5[CF] = n_sm * per_sm;
+    }
     const size_t atab = w5::ATAB_FLOATS * sizeof(float);
     if ((e = plan_one(w5::p25_ddc5_warp_kernel<U8, true>, 32 * w5::WARPS, sizeof(w5::WarpSm<U8, true>) * w5::WARPS + atab, n_sm, &plan->grid_w5m[U8])) != cudaSuccess) return e;
     if ((e = plan_one(w5::p25_ddc5_warp_kernel<CF, true>, 32 * w5::WARPS, sizeof(w5::WarpSm<CF, true>) * w5::WARPS + atab, n_sm, &plan->grid_w5m[CF])) != cudaSuccess) return e;
