@@ -196,7 +196,7 @@ constexpr int WS = 16;                 // window slots per class: 15 taps + one 
 constexpr int HTX = 27648;             // carried input tail (>= LE + (WARM + 1) * M + 64, a multiple of 128)
 constexpr int EARLY = 64;              // a window's newest sample lies at most this far ahead of n_m (a warp spans 62)
 constexpr int ROWS = (N + EARLY) / 2;  // tap rows per CTA: d0 = 2 row - EARLY + (1 - b), d0 in [-EARLY, N)
-constexpr int FSK = H + H / 8;         // a time's FFT buffer with one pad element per eight (see skew())
+constexpr int FSK = H + H / 8;         // a time's FFT buffer with pad elements (see skew_a(), skew_b())
 static_assert(HTX >= LE + (WARM + 1) * M + EARLY && HTX % 128 == 0, "warm-up windows must lie inside the carried tail");
 static_assert(M < N && N - M - 62 > 0, "a class receives at most one new sample per output time");
 
@@ -208,7 +208,7 @@ struct SmemC {
     float hist[P25_BOXCAR - 1][H];     // the nine discriminator values before the current batch, per channel of this CTA
     unsigned long long mbar[2];        // one transaction barrier per incoming buffer
     float4 twB[8][8];                  // w = exp(+2 pi i k r / 64) at [r][k], as {w, i w} (cmulw)
-    float4 twC[12][64];                // w = exp(+2 pi i j r / 768) at [r][j]
+    float2 twC[12][64];                // w = exp(+2 pi i j r / 768) at [r][j]
 };
 
 struct PfbParams {
@@ -232,7 +232,13 @@ __device__ __forceinline__ float2 load_logical(const float2* __restrict__ tail, 
     const float2* ptr = in_chunk ? chunk + (l - HTX) : tail + l;
     return (l >= 0 && l < HTX + n) ? __ldg(ptr) : make_float2(0.f, 0.f);
 }
-__device__ __forceinline__ int skew(int i) { return i + (i >> 3); }
+// Padded positions inside a time's FFT buffer, chosen so that BOTH sides of every pass are free of bank conflicts:
+//   pass A writes 8 j + q (lanes: j) and pass B reads j + 96 r (lanes: j) through skew_a: one pad per 16 elements;
+//   pass B writes 64 a + k + 8 q (lanes: a, k) and pass C reads j + 64 r (lanes: j) through skew_b: 8 pads per 64.
+// (One pad per eight for both, the first version, made every read span an extra wavefront: 9 % of the kernel's
+// shared-memory traffic, which is what bounds it.)
+__device__ __forceinline__ int skew_a(int i) { return i + (i >> 4); }
+__device__ __forceinline__ int skew_b(int i) { return i + 8 * (i >> 6); }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 // the partner CTA's copy of a shared-memory address of this CTA
 __device__ __forceinline__ unsigned map_to_rank(unsigned addr, unsigned rank) {
@@ -361,7 +367,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_ker
         sm.tab[g][row] = make_float4(t[0], t[1], t[2], t[3]);
     }
     if (tid < 64) sm.twB[tid >> 3][tid & 7] = twiddle4(p.twiddle[24 * (tid >> 3) * (tid & 7)]);
-    for (int i = tid; i < 12 * 64; i += NTH) sm.twC[i >> 6][i & 63] = twiddle4(p.twiddle[2 * (i >> 6) * (i & 63)]);
+    for (int i = tid; i < 12 * 64; i += NTH) sm.twC[i >> 6][i & 63] = p.twiddle[2 * (i >> 6) * (i & 63)];
 #pragma unroll
     for (int i = 0; i < P25_BOXCAR - 1; i++) sm.hist[i][tid] = 0.f;
     // this thread's channel: k' = 384 b + kq (the 384 radix-2 pairs this CTA combines), channel k' or k' + 768
@@ -449,7 +455,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_ker
             __syncthreads();
             dft8(v);
 #pragma unroll
-            for (int q = 0; q < 8; q++) sm.f0[tt][skew(8 * j + q)] = v[q];
+            for (int q = 0; q < 8; q++) sm.f0[tt][skew_a(8 * j + q)] = v[q];
         }
         __syncthreads();
         // ---- pass B: radix 8, stride 8
@@ -457,14 +463,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_ker
             const int tt = tid / 96, j = tid - 96 * tt, k = j & 7;
             float2 v[8];
 #pragma unroll
-            for (int r = 0; r < 8; r++) v[r] = sm.f0[tt][skew(j + 96 * r)];
+            for (int r = 0; r < 8; r++) v[r] = sm.f0[tt][skew_a(j + 96 * r)];
             __syncthreads();
 #pragma unroll
             for (int r = 1; r < 8; r++) v[r] = cmulw(v[r], sm.twB[r][k]);
             dft8(v);
             const int j0 = (j >> 3) * 64 + k;
 #pragma unroll
-            for (int q = 0; q < 8; q++) sm.f0[tt][skew(j0 + 8 * q)] = v[q];
+            for (int q = 0; q < 8; q++) sm.f0[tt][skew_b(j0 + 8 * q)] = v[q];
         }
         __syncthreads();
         // ---- pass C: radix 12, stride 64 (512 butterflies).  Outputs k' = j + 64 q: q < 6 lies in CTA 0's combine range,
@@ -474,9 +480,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1) p25_pfbc_ker
         if (tid < TB * 64) {
             const int tt = tid >> 6, j = tid & 63;
             float2 v[12];
-            v[0] = sm.f0[tt][skew(j)];
+            v[0] = sm.f0[tt][skew_b(j)];
 #pragma unroll
-            for (int r = 1; r < 12; r++) v[r] = cmulw(sm.f0[tt][skew(j + 64 * r)], sm.twC[r][j]);
+            for (int r = 1; r < 12; r++) {
+                const float2 w = sm.twC[r][j];                     // 8-byte entries: i w is formed in registers
+                v[r] = cmulw(sm.f0[tt][skew_b(j + 64 * r)], make_float4(w.x, w.y, -w.y, w.x));
+            }
             dft12(v);
             const unsigned rbase = inc_remote + (unsigned)((((nb & 1) * TB + tt) * (H / 2) + j) * sizeof(float2));
             const unsigned rmbar = mbar_remote + (unsigned)((nb & 1) * sizeof(unsigned long long));

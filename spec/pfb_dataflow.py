@@ -26,8 +26,14 @@ ROWS = (N + EARLY) // 2
 HTX = 27648                # carried input tail: >= LE + (WARM + 1) * M + EARLY, a multiple of 128
 
 
-def skew(i):
-    return i + (i >> 3)
+def skew_a(i):
+    """Position of element i in the buffer between passes A and B (one pad per 16)."""
+    return i + (i >> 4)
+
+
+def skew_b(i):
+    """Position of element i in the buffer between passes B and C (8 pads per 64)."""
+    return i + 8 * (i >> 6)
 
 
 def tap_table(heq: np.ndarray, b: int) -> np.ndarray:

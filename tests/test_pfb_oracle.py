@@ -90,6 +90,20 @@ def test_kernel_dataflow_equals_the_definition():
     rng = np.random.default_rng(0)
     v = rng.standard_normal(768) + 1j * rng.standard_normal(768)
     assert np.max(np.abs(df.idft768(v) - np.fft.ifft(v) * 768)) < 1e-10
+    # the padded buffer layouts: injective, inside the buffer, and free of bank conflicts on both sides of each pass
+    # (a half-warp's sixteen 8-byte accesses must fall into sixteen different bank pairs)
+    idx = np.arange(768)
+    for f in (df.skew_a, df.skew_b):
+        assert len(set(f(idx))) == 768 and f(idx).max() < 768 + 768 // 8
+    banks = lambda pos: len(set(int(x) % 16 for x in pos))
+    for j0 in range(0, 96, 16):
+        j = np.arange(j0, j0 + 16)
+        assert all(banks(df.skew_a(8 * j + q)) == 16 for q in range(8))                       # pass A writes
+        assert all(banks(df.skew_a(j + 96 * r)) == 16 for r in range(8))                      # pass B reads
+        assert all(banks(df.skew_b((j >> 3) * 64 + (j & 7) + 8 * q)) == 16 for q in range(8))  # pass B writes
+    for j0 in range(0, 64, 16):
+        j = np.arange(j0, j0 + 16)
+        assert all(banks(df.skew_b(j + 64 * r)) == 16 for r in range(12))                     # pass C reads
     heq = po.equivalent_prototype()
     x = rng.standard_normal(36 * 400 + 123) + 1j * rng.standard_normal(36 * 400 + 123)
     ref = po.channelize_fused(x)
