@@ -875,34 +875,58 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
             // one sample, which makes every packed operand an aligned register pair) and the second half of each
             // load is reused by the next tap group: 2 LDS.128 per 16 FFMA2 instead of 16 LDS.32.  Each position's sum
             // still runs over k = 0 .. 230 in order with one fmaf per tap, exactly like the oracle.
-            const unsigned long long pos = ws.pos;
+            unsigned long long pos = ws.pos;
             if (pos >= end) break;
-            const long long wbase = (long long)(pos - p0) + P25CU_BB_HIST - (P25_FP_LEN - 1);   // row index of win[0]
             const long long wlim = (long long)P25CU_BB_HIST + (long long)p.n;                   // first invalid row index
             float* win1 = win + WIN_PAD;
-            __syncwarp();
-            for (int i = lane; i < WIN_PAD; i += 32) {
-                const float v = (i < WIN_LEN && wbase + i < wlim) ? __ldg(row + wbase + i) : 0.f;
-                win[i] = v;
-                if (i) win1[i - 1] = v;
-            }
-            if (lane < 5 && wbase + WIN_LEN + 32 * lane < wlim) prefetch_l1(row + wbase + WIN_LEN + 32 * lane);   // next step's new samples
-            __syncwarp();
             // A stream that has just left a frame finds the next sync within a step or two: the prefilter only pays once the
-            // search has come up empty twice (idle and noise-only channels then never run the exact correlator again).
-            // It reads the staged window: fragments straight from the row through L1 measured slower.
-            if (PRE && ws.quiet >= P25_PREFILTER_QUIET && !sync_prefilter(win, sh.fpb, sh.pe[warp], lane)) {
-                // no position of this step can be above threshold: the detector's carried state is "previous not above"
-                // (prev_corr is only ever compared when the previous position was above)
-                const unsigned long long left0 = end - pos;
-                __syncwarp();
-                if (lane == 0) {
-                    ws.prev_above = 0;
-                    ws.have_prev = 1;
-                    ws.pos = pos + (left0 < SEARCH_N ? left0 : SEARCH_N);
+            // search has come up empty twice.  From then on an idle or noise-only channel stays in this loop -- stage one
+            // copy of the window, fifteen tensor steps, next 128 positions -- and never runs the exact correlator again;
+            // a step without a candidate leaves the detector's carried state at "previous not above" (prev_corr is only
+            // ever compared when the previous position was above).
+            if (PRE && ws.quiet >= P25_PREFILTER_QUIET) {
+                const unsigned long long pos_in = pos;
+                bool hit = false;
+                while (pos < end) {
+                    const long long wb = (long long)(pos - p0) + P25CU_BB_HIST - (P25_FP_LEN - 1);
+                    // start the staged window on a 16-byte boundary of the row (three LDG.128 per lane instead of twelve
+                    // LDG.32): the tile then begins up to three positions early -- testing a position twice is harmless
+                    const int o = (int)(wb & 3);
+                    const bool vec = wb - o + WIN_PAD <= wlim;
+                    __syncwarp();
+                    if (vec) {
+                        const float4* src = reinterpret_cast<const float4*>(row + (wb - o));
+                        for (int i = lane; i < WIN_PAD / 4; i += 32) reinterpret_cast<float4*>(win)[i] = __ldg(src + i);
+                    } else {
+                        for (int i = lane; i < WIN_PAD; i += 32) win[i] = (i < WIN_LEN && wb + i < wlim) ? __ldg(row + wb + i) : 0.f;
+                    }
+                    __syncwarp();
+                    hit = sync_prefilter(win, sh.fpb, sh.pe[warp], lane);
+                    if (hit) break;
+                    const unsigned long long left0 = end - pos, step = (unsigned long long)(SEARCH_N - (vec ? o : 0));
+                    pos += left0 < step ? left0 : step;
                 }
+                if (pos != pos_in) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        ws.prev_above = 0;
+                        ws.have_prev = 1;
+                        ws.pos = pos;
+                    }
+                    __syncwarp();
+                }
+                if (!hit) break;                                   // the chunk is exhausted
+            }
+            {   // a candidate (or a stream that is not idle): both copies of the window at pos for the exact correlator
+                const long long wbase = (long long)(pos - p0) + P25CU_BB_HIST - (P25_FP_LEN - 1);   // row index of win[0]
                 __syncwarp();
-                continue;
+                for (int i = lane; i < WIN_PAD; i += 32) {
+                    const float v = (i < WIN_LEN && wbase + i < wlim) ? __ldg(row + wbase + i) : 0.f;
+                    win[i] = v;
+                    if (i) win1[i - 1] = v;
+                }
+                if (lane < 5 && wbase + WIN_LEN + 32 * lane < wlim) prefetch_l1(row + wbase + WIN_LEN + 32 * lane);   // next step's new samples
+                __syncwarp();
             }
             float2 c01 = make_float2(0.f, 0.f), c23 = c01, e01 = c01, e23 = c01;   // positions h = 0,1 | 2,3
             {
