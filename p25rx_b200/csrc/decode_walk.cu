@@ -125,11 +125,25 @@ __device__ __noinline__ bool sync_prefilter(const float* __restrict__ win, const
     const float2* wa = reinterpret_cast<const float2*>(win + 8 * g + 2 * t);   // A[g][2t, 2t+1] of step 0; row g + 8 is 64 samples on
     const unsigned* fb = fpb + 8 + 2 * t - g;                                     // B[2t, 2t+1][g] of step 0: (fp[2t - g], fp[2t + 1 - g])
     float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 5
-    for (int s = 0; s < 15; s++) {
-        const float2 x0 = wa[8 * s], x1 = wa[8 * s + 32], x2 = wa[8 * s + 4], x3 = wa[8 * s + 36];
-        const unsigned a[4] = {pack_bf16(x0.x, x0.y), pack_bf16(x1.x, x1.y), pack_bf16(x2.x, x2.y), pack_bf16(x3.x, x3.y)};
-        mma_bf16(c, a, fb[16 * s], fb[16 * s + 8]);
+    // rows g + 8 of step s are rows g of step s + 4 (the window moves 8 samples per row, 16 per step ... 64 = 4 steps):
+    // every fragment register is loaded and packed once and used twice, 38 instead of 60 shared-memory loads per tile
+    unsigned q0[19], q2[19];
+#pragma unroll
+    for (int s = 0; s < 19; s++) {
+        if (s < 4) {
+            const float2 x0 = wa[8 * s], x2 = wa[8 * s + 4];
+            q0[s] = pack_bf16(x0.x, x0.y);
+            q2[s] = pack_bf16(x2.x, x2.y);
+        }
+        if (s + 4 < 19) {
+            const float2 x0 = wa[8 * (s + 4)], x2 = wa[8 * (s + 4) + 4];
+            q0[s + 4] = pack_bf16(x0.x, x0.y);
+            q2[s + 4] = pack_bf16(x2.x, x2.y);
+        }
+        if (s < 15) {
+            const unsigned a[4] = {q0[s], q0[s + 4], q2[s], q2[s + 4]};
+            mma_bf16(c, a, fb[16 * s], fb[16 * s + 8]);
+        }
     }
     __syncwarp();
     const float l0 = pe[g + 27] - pe[g], l1 = pe[g + 35] - pe[g + 8];   // blocks a + 1 .. a + 27 lie inside every window of row a
@@ -897,6 +911,8 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
                     if (vec) {
                         const float4* src = reinterpret_cast<const float4*>(row + (wb - o));
                         for (int i = lane; i < WIN_PAD / 4; i += 32) reinterpret_cast<float4*>(win)[i] = __ldg(src + i);
+                        // the next step's 128 new samples: in flight while this step computes (the row comes from HBM)
+                        if (lane < 5 && wb - o + WIN_PAD + 32 * lane < wlim) prefetch_l1(row + (wb - o) + WIN_PAD + 32 * lane);
                     } else {
                         for (int i = lane; i < WIN_PAD; i += 32) win[i] = (i < WIN_LEN && wb + i < wlim) ? __ldg(row + wb + i) : 0.f;
                     }
