@@ -45,7 +45,7 @@ __constant__ float c_sync_fp[P25_FP_LEN];
 //     (216 of the 231 samples), from block energies and one warp prefix sum.
 // Testing corr' > 0 && corr'^2 >= (rho - 0.02)^2 |fp|^2 en_low can therefore only err towards running the exact correlator.
 #ifndef P25_PREFILTER_QUIET
-#define P25_PREFILTER_QUIET 2                 // empty search steps in a row before the prefilter is consulted
+#define P25_PREFILTER_QUIET 0                 // empty search steps in a row before the prefilter is consulted (A/B: 0 is best where it is used)
 #endif
 #define P25_PREFILTER_RHO2_EFP (P25_SYNC_RHO2_EFP * (0.63f * 0.63f) / (0.65f * 0.65f))
 
@@ -893,12 +893,11 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
             if (pos >= end) break;
             const long long wlim = (long long)P25CU_BB_HIST + (long long)p.n;                   // first invalid row index
             float* win1 = win + WIN_PAD;
-            // A stream that has just left a frame finds the next sync within a step or two: the prefilter only pays once the
-            // search has come up empty twice.  From then on an idle or noise-only channel stays in this loop -- stage one
+            // An idle or noise-only channel stays in this loop -- stage one
             // copy of the window, fifteen tensor steps, next 128 positions -- and never runs the exact correlator again;
             // a step without a candidate leaves the detector's carried state at "previous not above" (prev_corr is only
             // ever compared when the previous position was above).
-            if (PRE && ws.quiet >= P25_PREFILTER_QUIET) {
+            if (PRE && (int)ws.quiet >= P25_PREFILTER_QUIET) {
                 const unsigned long long pos_in = pos;
                 bool hit = false;
                 while (pos < end) {
