@@ -356,7 +356,7 @@ extern "C" int p25cu_demod(p25cu_ctx* ctx, const void* iq, size_t n, int iq_on_d
     const bool timed = ctx->timing && n && ctx->n_timed < 128;
     if (timed) CK(cudaEventRecord(ctx->tev[2 * ctx->n_timed], ctx->stream));
     if (n && ctx->n_captures) {
-        // wideband capture -> 1,536 channels per capture (pfb.cu): discriminator rows, per-channel baseband, carried state
+        // wideband capture -> 1,536 channels per capture (pfb.cu): one cluster kernel writes the per-channel baseband rows; the carried state is the input tail
         const size_t ch = p25cu_pfb_channels();
         unsigned nl = 0;
         if (ctx->keep_spectra && !ctx->d_y) CK(cudaMalloc(&ctx->d_y, (size_t)ctx->n_captures * ctx->y_rows * ch * sizeof(float2)));
