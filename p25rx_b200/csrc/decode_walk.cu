@@ -63,8 +63,6 @@ struct WalkShared {
     unsigned surv[P25CU_WALK_WARPS][52];        // 3/4-rate trellis survivors: 8 states x 3 bits per step
     unsigned short pn_a[116], pn_c[116];        // IMBE PN generator n steps ahead: p_n = pn_a[n] * p_0 + pn_c[n] (mod 2^16)
     unsigned char imbe_src[8 * 24];             // inverse of the IMBE interleave schedule: [code word][bit] -> frame bit
-    unsigned fpb[FPB_LEN];                      // sync fingerprint as BF16 pairs: fpb[i] = (fp[i - 8], fp[i - 7]), zeros outside (sync_prefilter)
-    float pe[P25CU_WALK_WARPS][48];             // prefix sums of the 8-sample block energies of the staged window
 };
 
 // packed pair of IEEE fused multiply-adds (one FFMA2): each half is exactly fmaf()
@@ -261,17 +259,14 @@ __device__ __forceinline__ void nid_apply(const WarpCtx& c, unsigned long long i
 // syndrome is non-zero, the Chien search covers two positions per lane.  Same bounded-distance result as
 // p25_bch_decode (the per-thread form used by the unit kernels).  Returns corrected bits or -1, uniformly.
 __device__ __forceinline__ unsigned warp_bch_syndromes(const P25DevTables& T, unsigned long long w, int lane) {
-    const int j = lane + 1;
-    int acc = 0, e = 0;
+    // S_j = r(alpha^j) over GF(64) is linear in the received bits: each of its six bits is the parity of the word under a
+    // fixed mask (p25_fill_tables) -- 6 AND + POPC pairs per lane instead of a 63-step loop over the bits
+    unsigned acc = 0;
     if (lane < 2 * P25_BCH_T) {
-        for (int i = 0; i < 63; i++) {
-            if ((w >> i) & 1) acc ^= T.gf_exp[e];
-            e += j;
-            if (e >= 63) e -= 63;
-            if (e >= 63) e -= 63;
-        }
+#pragma unroll
+        for (int b = 0; b < 6; b++) acc |= (unsigned)(__popcll(w & T.bch_par[lane][b]) & 1) << b;
     }
-    return (unsigned)acc;
+    return acc;
 }
 
 __device__ __noinline__ int warp_bch_decode(const P25DevTables& T, unsigned char* scratch, unsigned long long word63, int lane,
@@ -825,10 +820,7 @@ __device__ __forceinline__ void walk_shared_init(WalkShared& sh, const P25DevTab
         }
     }
     for (unsigned i = threadIdx.x; i < 144; i += blockDim.x) sh.imbe_src[tables->imbe_cw[i] * 24 + tables->imbe_bit[i]] = (unsigned char)i;
-    for (int i = threadIdx.x; i < FPB_LEN; i += blockDim.x) {
-        const float lo = (i >= 8 && i < 8 + P25_FP_LEN) ? c_sync_fp[i - 8] : 0.f, hi = (i >= 7 && i < 7 + P25_FP_LEN) ? c_sync_fp[i - 7] : 0.f;
-        sh.fpb[i] = pack_bf16(lo, hi);
-    }
+
 }
 // PRE: consult the tensor-pipe prefilter before the exact correlator (contexts whose streams are mostly idle: the
 // channelizer's 1,536 slots per capture).  Decoded output is identical either way; where every stream carries a signal
@@ -838,6 +830,22 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
     __shared__ WalkShared sh;
     walk_shared_init(sh, p.tables);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // The prefilter's operands exist only in the instantiation that uses it: beside the /50 demod kernel (3 x 68,096 bytes
+    // of dynamic shared memory + 1 KB per CTA of system use, 228 KB per SM) two walker CTAs have 12,032 bytes each --
+    // p25_walk_kernel<false> must stay below that or the co-running pair no longer fits one SM.
+    static_assert(sizeof(WalkShared) <= 12032, "p25_walk_kernel<false> has to fit beside three /50 demod CTAs, twice");
+    const unsigned* fpb = nullptr;
+    float* pe = nullptr;
+    if constexpr (PRE) {
+        __shared__ unsigned s_fpb[FPB_LEN];          // sync fingerprint as BF16 pairs: (fp[i - 8], fp[i - 7]), zeros outside
+        __shared__ float s_pe[P25CU_WALK_WARPS][48];   // prefix sums of the 8-sample block energies of the staged window
+        for (int i = threadIdx.x; i < FPB_LEN; i += blockDim.x) {
+            const float lo = (i >= 8 && i < 8 + P25_FP_LEN) ? c_sync_fp[i - 8] : 0.f, hi = (i >= 7 && i < 7 + P25_FP_LEN) ? c_sync_fp[i - 7] : 0.f;
+            s_fpb[i] = pack_bf16(lo, hi);
+        }
+        fpb = s_fpb;
+        pe = s_pe[warp];
+    }
     WalkState& ws = sh.ws[warp];
     __syncthreads();                                          // tables staged
     // grid-stride over the streams: one pass when the grid covers them all (the usual launch), several when the walker
@@ -916,7 +924,7 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
                         for (int i = lane; i < WIN_PAD; i += 32) win[i] = (i < WIN_LEN && wb + i < wlim) ? __ldg(row + wb + i) : 0.f;
                     }
                     __syncwarp();
-                    hit = sync_prefilter(win, sh.fpb, sh.pe[warp], lane);
+                    hit = sync_prefilter(win, fpb, pe, lane);
                     if (hit) break;
                     const unsigned long long left0 = end - pos, step = (unsigned long long)(SEARCH_N - (vec ? o : 0));
                     pos += left0 < step ? left0 : step;

@@ -46,6 +46,7 @@ struct alignas(16) P25DevTables {
     uint8_t imbe_cw[144];
     uint8_t imbe_bit[144];
     uint8_t imbe_cw_bits[8];
+    uint64_t bch_par[22][6];    // BCH(63,16,23) syndromes as parities: bit b of S_j = parity(word & bch_par[j - 1][b])
 };
 
 static inline void p25_fill_tables(P25DevTables* t) {
@@ -62,6 +63,13 @@ static inline void p25_fill_tables(P25DevTables* t) {
         t->trellis_pair[i] = P25_CONSTELLATION[P25_TRELLIS_HALF[i]];
     }
     for (int i = 0; i < 64; i++) t->trellis34_pair[i] = P25_CONSTELLATION[P25_TRELLIS_3_4[i]];
+    for (int j = 1; j <= 22; j++)           // S_j = sum_i r_i alpha^(j i): bit b of alpha^(j i) selects r_i into parity b
+        for (int b = 0; b < 6; b++) {
+            uint64_t m = 0;
+            for (int i = 0; i < 63; i++)
+                if ((P25_GF_EXP[(j * i) % 63] >> b) & 1) m |= (uint64_t)1 << i;
+            t->bch_par[j - 1][b] = m;
+        }
     for (int i = 0; i < 128; i++) t->gf_exp[i] = P25_GF_EXP[i];
     for (int i = 0; i < 64; i++) t->gf_log[i] = P25_GF_LOG[i];
     for (int i = 0; i < 8; i++) {
