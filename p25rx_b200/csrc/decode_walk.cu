@@ -1145,8 +1145,11 @@ __global__ void __launch_bounds__(32 * P25CU_WALK_WARPS, 16) p25_walk_kernel(con
             if (st == WS_FLUSH) {
                 if (lane == 0) enter_sync(ws, idx + 1);
             } else if (st == WS_NID) {
-                unsigned long long bits = 0;
-                for (int i = 0; i < P25_NID_DIBITS; i++) bits = (bits << 2) | ws.buf[i];
+                // the 64 NID bits, dibit i at bits 63 - 2 i .. 62 - 2 i: one dibit per lane, two warp OR-reductions
+                static_assert(P25_NID_DIBITS == 32, "one NID dibit per lane");
+                const unsigned long long mine = (unsigned long long)(ws.buf[lane] & 3u) << (2 * (31 - lane));
+                const unsigned long long bits = ((unsigned long long)__reduce_or_sync(FULL, (unsigned)(mine >> 32)) << 32) |
+                                                __reduce_or_sync(FULL, (unsigned)mine);
                 unsigned data = 0;
                 const int nerr = warp_bch_decode(sh.T, sh.scr[warp], bits >> 1, lane, &data);
                 if (lane == 0) nid_apply(c, idx, nerr, data);
