@@ -1373,6 +1373,358 @@ __global__ void __launch_bounds__(32 * WARPS, Fmt<FMT>::MINB) p25_ddc5_warp_kern
 
 }  // namespace w5
 
+
+// =====================================================================================================
+// /5 warp kernel for u8 input with the DECIMATOR ON THE INTEGER TENSOR PIPE (round 2; VERDICT r1 item 4: "integer-domain
+// decimator on the raw bytes").  The warp kernel above is bound by the FP32 pipe: 21 of its 62 FIR FFMA2 per output are
+// the /5 decimator, and every input byte costs two PRMT + half a FADD2 before it can enter an FFMA2.  Here the raw bytes
+// go into mma.sync.m16n8k32.s32.u8.s8 as they lie in the TMA-staged slice, without any conversion:
+//   * A (16 x 32 bytes per k-step) = sixteen overlapping rows of the slice, row m starting 40 samples (80 bytes) after
+//     row m - 1, interleaved I/Q bytes along k; a row's 64-sample window holds the inputs of eight consecutive outputs;
+//   * B = the taps as a banded matrix: column 2 n' + c (output n', component c) has tap k = 24 - d at the byte of sample
+//     skew + 5 n + d, component c, zero elsewhere.  The taps are 24-bit fixed point, t = round(h 2^25) (an error of
+//     2^-26 per tap, the spacing of fp32 at the largest tap), split into three balanced s8 limbs -> three products
+//     with s32 accumulators; two n-tiles (outputs 0..3 | 4..7 of every row) x three k-steps each x three limbs =
+//     18 IMMA per 128 outputs, 8.35 clocks each per sub-core beside an FFMA2 stream that keeps 85 % of its peak
+//     (profiles/pipe_peaks_r02.json);
+//   * the sums are exact integers.  The accumulators start at the bit pattern of 1.5 * 2^23 minus 128 * (sum of the
+//     limb), so they ARE the floats 1.5 * 2^23 + sum l (u - 128): one FADD2 per limb and two FFMA2 give
+//     y = 2^16 s2 + 2^8 s1 + s0 with a single rounding (I2F runs at 32 per clock per SM: not an option).  y is the
+//     decimator output in byte units x 2^25; the discriminator does not see the scale, dc and the power scale carry it.
+//   * the stream's alignment inside its 16-byte group (skew = 4 a + sk) is constant over a launch: a shifts the row
+//     pointers by 8 bytes, sk selects one of four B tables (a window holds sk + 60 <= 63 samples).
+//   * the k index is permuted so that a lane's eight words of a row are four 8-byte loads, and mma row g reads slice
+//     row 2 (g & 3) + (g >> 2): both halves of the warp then hit 32 different banks (row stride 20 words).
+// 128 outputs per iteration on all 32 lanes (no ghost lane); everything after the decimator is the warp kernel's code.
+// =====================================================================================================
+namespace w5i {
+
+using fast::mbar_init;
+using fast::mbar_expect_tx;
+using fast::mbar_wait;
+using fast::tma_load_1d;
+using fast::cfma;
+using fast5::add2;
+using fast5::disc_atan2_pair;
+
+constexpr int R = 8;                                    // outputs per lane
+constexpr int NOUT = 32 * R;                            // 256 outputs per warp iteration: two m-tiles of 16 rows x 8 outputs
+constexpr int XNEW = 5 * NOUT;                          // 1280 fresh input samples (2560 bytes: the skew never changes)
+constexpr int XREAD = 5 * (NOUT - 1) + P25_TAPS_DECIM;  // 1300 samples read
+constexpr int WARPS = 4;
+constexpr int AL = 8, ES = 2;
+constexpr int XLEN = (XREAD + 2 * AL - 2) / AL * AL;    // 1312
+constexpr int XBYTES = (XLEN * ES + 127) / 128 * 128;   // 2688
+constexpr int MINB = 4;
+constexpr int HROWS = (P25_TAPS_CHAN - 1) / R;          // 5 history rows (of eight) of the decimator output
+constexpr int YROWS = HROWS + 32;                       // 37 rows x 4 words = 4 (mod 8) words between the four arrays
+constexpr int DROWS = 2;                                // history rows of the discriminator output (>= 9 samples)
+constexpr int NB = 18;                                  // B fragments: [n-tile][k-step - n-tile][limb]
+constexpr int SCALE_LOG2 = 25;                          // taps as round(h * 2^25): |t| < 2^23
+static_assert(XLEN * ES >= 80 * 31 + 8 + 128 && XNEW % (2 * AL) == 0, "A rows inside the slice; constant skew");
+static_assert((P25_TAPS_CHAN - 1) % R == 0 && DROWS * R >= P25_BOXCAR - 1 && (YROWS * 4) % 8 == 4, "history rows, store banks");
+
+// decimator outputs as rows of eight, split over four arrays of 16-byte pairs: yd[q][i] = (y[8 i + 2 q], y[8 i + 2 q + 1]).
+// A lane's 48-sample channel-filter window is 24 LDS.128 at a 16-byte lane stride (no conflicts), and the fragment
+// stores of the decimator (below) hit 32 different banks.
+struct __align__(128) WarpSm {
+    unsigned char xs[2][XBYTES];
+    float4 yd[4][YROWS];
+    float4 dA[DROWS + 32], dB[DROWS + 32];      // discriminator outputs: (d[8 i .. 8 i + 3]) | (d[8 i + 4 .. 8 i + 7])
+    unsigned long long full[2];
+};
+
+__device__ uint2 g_btab[4][NB][32];             // [sk][fragment][lane] = (b0, b1)
+
+__device__ __forceinline__ void imma(int (&d)[4], const unsigned (&a)[4], const uint2 b) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+// first k-step of a chain: the start value (one register for all four accumulators) is the C operand
+__device__ __forceinline__ void imma0(int (&d)[4], const unsigned (&a)[4], const uint2 b, const int c) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y), "r"(c));
+}
+// 4-byte shared-memory load the compiler may not fuse with its neighbour (an 8-byte load would need four moves to put
+// the words into the fragment's register order)
+__device__ __forceinline__ unsigned lds32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void issue_slice(WarpSm& sm, int stage, int ht, int lend, const unsigned char* tail,
+                                            const unsigned char* chunk, int l0) {
+    const int la = l0 & ~(AL - 1);
+    const int lb = min(la + XLEN, lend);
+    if (la >= ht) {
+        const unsigned bytes = (unsigned)(lb - la) * ES;
+        mbar_expect_tx(&sm.full[stage], bytes);
+        tma_load_1d(&sm.xs[stage][0], chunk + (size_t)(la - ht) * ES, bytes, &sm.full[stage]);
+        return;
+    }
+    const int t1 = min(lb, ht);
+    const unsigned nt = (unsigned)(t1 - la), nc = (unsigned)(lb - t1);
+    mbar_expect_tx(&sm.full[stage], (nt + nc) * ES);
+    tma_load_1d(&sm.xs[stage][0], tail + (size_t)la * ES, nt * ES, &sm.full[stage]);
+    if (nc) tma_load_1d(&sm.xs[stage][nt * ES], chunk, nc * ES, &sm.full[stage]);
+}
+
+__global__ void __launch_bounds__(32 * WARPS, MINB) p25_ddc5_imma_kernel(const DdcParams p, const unsigned its_per_stream,
+                                                                         const float dc, const float pw_scale,
+                                                                         const int init0, const int init1, const int init2) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSm& sm = reinterpret_cast<WarpSm*>(smem_raw)[warp];
+    uint2* const btab = reinterpret_cast<uint2*>(smem_raw + sizeof(WarpSm) * WARPS);
+    const int ips = (int)its_per_stream, ht = (int)p.ht, lend = (int)p.ht + (int)p.n, n_out = (int)p.n_out;
+    const int l_base = (int)(5 * (long long)p.m0 - (long long)p.a0) - 20 + ht;   // logical index of iteration 0's first input
+    const int skew = l_base & (AL - 1);                     // the same for every iteration of every stream
+    for (int e = threadIdx.x; e < NB * 32; e += 32 * WARPS) btab[e] = (&g_btab[skew & 3][0][0])[e];
+    if (lane == 0) {
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = lane; i < 4 * YROWS; i += 32) (&sm.yd[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < DROWS + 32; i += 32) sm.dA[i] = sm.dB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+
+    const unsigned gw = blockIdx.x * WARPS + warp, GW = gridDim.x * WARPS;
+    const unsigned long long total = (unsigned long long)p.n_streams * its_per_stream;
+    const unsigned long long b0 = total * gw / GW, b1 = total * (gw + 1ull) / GW;
+    if (b0 >= b1) return;
+    const size_t row_bytes = (size_t)p.n * ES, tail_bytes = (size_t)p.ht * ES;
+    const bool want_pw = p.power_sum != nullptr;
+    unsigned s = (unsigned)(b0 / its_per_stream);
+    int it_first = (int)(b0 % its_per_stream);
+    unsigned left = (unsigned)(b1 - b0);
+    const unsigned char* chunk = (const unsigned char*)p.iq + s * row_bytes;
+    const unsigned char* tail = (const unsigned char*)p.tail_in + s * tail_bytes;
+    if (lane == 0) {
+        issue_slice(sm, 0, ht, lend, tail, chunk, l_base + XNEW * (it_first - 1));
+        issue_slice(sm, 1, ht, lend, tail, chunk, l_base + XNEW * it_first);
+    }
+    // fragment geometry: mma rows g and g + 8 of m-tile mt read slice rows 16 mt + drow and + 8; a lane's words of a
+    // k-step are t and t + 4 of its eight (row stride 20 words: 32 different banks for any row permutation); the row
+    // permutation puts the half-warps' stores on rows {0, 2, 4, 6} / {1, 3, 5, 7} (+ 8, + 16 ...) of two arrays each
+    const int g = lane >> 2, tig = lane & 3;
+    const int drow = ((g & 3) << 1) | (g >> 2);
+    const unsigned a_off = 80u * drow + 8u * (skew >> 2) + 4u * tig;
+    const uint2* const bl = btab + lane;
+    float2* const ydst = reinterpret_cast<float2*>(&sm.yd[tig >> 1][HROWS + drow]) + (tig & 1);
+    const float2 unmagic = make_float2(-12582912.f, -12582912.f);
+    float2 c_carry = make_float2(0.f, 0.f);
+    unsigned use = 0;
+
+    while (left) {
+      const int n_st = min(ips - it_first, (int)left);
+      const int npiece = n_st + 1;
+      left -= (unsigned)n_st;
+      float* const out_lane = p.bb + (size_t)s * p.row_stride + P25CU_BB_HIST + R * lane;
+      float pw = 0.f;
+      for (int j = 0; j < npiece; j++, use++) {
+        const int it = it_first - 1 + j;
+        const int stage = use & 1;
+        const int nv = j ? min(n_out - NOUT * it, NOUT) : 0;
+        mbar_wait(&sm.full[stage], (use >> 1) & 1);
+
+        // ---- /5 decimator on the integer tensor pipe: 36 IMMA, every B fragment loaded once for both m-tiles
+        {
+            int acc[2][2][3][4];
+            const int init[3] = {init0, init1, init2};
+            const unsigned xa = fast::smem_u32(sm.xs[stage]) + a_off;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+                unsigned a[2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    const unsigned ad = xa + 1280u * mt + 32u * ks;
+                    a[mt][0] = lds32(ad);
+                    a[mt][1] = lds32(ad + 640u);
+                    a[mt][2] = lds32(ad + 16u);
+                    a[mt][3] = lds32(ad + 656u);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) {
+                    const int jj = ks - nt;
+                    if (jj < 0 || jj > 2) continue;
+#pragma unroll
+                    for (int l = 0; l < 3; l++) {
+                        const uint2 b = bl[32 * ((nt * 3 + jj) * 3 + l)];
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++) {
+                            if (jj == 0) imma0(acc[mt][nt][l], a[mt], b, init[l]);
+                            else imma(acc[mt][nt][l], a[mt], b);
+                        }
+                    }
+                }
+            }
+            // (c0, c1) = (re, im) of output 128 mt + 8 drow + 4 nt + tig, (c2, c3) of that output + 64
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        float2 f[3];
+#pragma unroll
+                        for (int l = 0; l < 3; l++)
+                            f[l] = add2(make_float2(__int_as_float(acc[mt][nt][l][2 * h]), __int_as_float(acc[mt][nt][l][2 * h + 1])), unmagic);
+                        ydst[2 * (2 * nt * YROWS + 16 * mt + 8 * h)] = cfma(65536.f, f[2], cfma(256.f, f[1], f[0]));
+                    }
+        }
+        __syncwarp();                                                                 // S1: xs[stage] consumed, rows visible
+        if (lane == 0) {
+            if (j + 2 < npiece) issue_slice(sm, stage, ht, lend, tail, chunk, l_base + XNEW * (it + 2));
+            else if (left) issue_slice(sm, stage, ht, lend, tail + tail_bytes, chunk + row_bytes, l_base + XNEW * (j + 1 - npiece));
+        }
+
+        // ---- channel-select FIR: outputs 8 lane + r, window = rows lane .. lane + 5 (48 samples, s = 40 + r - k)
+        float2 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = make_float2(dc, dc);
+#pragma unroll
+        for (int t = 0; t <= HROWS; t++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 v = sm.yd[q][lane + t];
+                const float2 x0 = make_float2(v.x, v.y), x1 = make_float2(v.z, v.w);
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int k0 = (P25_TAPS_CHAN - 1) + r - (8 * t + 2 * q);
+                    if (k0 >= 0 && k0 < P25_TAPS_CHAN) acc[r] = cfma(c_taps_chan[k0], x0, acc[r]);
+                    if (k0 - 1 >= 0 && k0 - 1 < P25_TAPS_CHAN) acc[r] = cfma(c_taps_chan[k0 - 1], x1, acc[r]);
+                }
+            }
+        }
+        // ---- FM discriminator on the eight outputs in registers; the sample before comes from the lane below
+        float2 prev;
+        prev.x = __shfl_up_sync(0xFFFFFFFFu, acc[R - 1].x, 1);
+        prev.y = __shfl_up_sync(0xFFFFFFFFu, acc[R - 1].y, 1);
+        if (lane == 0) prev = c_carry;
+        c_carry.x = __shfl_sync(0xFFFFFFFFu, acc[R - 1].x, 31);
+        c_carry.y = __shfl_sync(0xFFFFFFFFu, acc[R - 1].y, 31);
+        float dd[R];
+#pragma unroll
+        for (int r = 0; r < R; r += 2) {
+            const float2 c0 = acc[r], c1 = acc[r + 1];
+            const float2 re = make_float2(c0.x * prev.x + c0.y * prev.y, c1.x * c0.x + c1.y * c0.y);
+            const float2 im = make_float2(c0.y * prev.x - c0.x * prev.y, c1.y * c0.x - c1.x * c0.y);
+            const float2 th = disc_atan2_pair(im, re);
+            dd[r] = th.x * P25_FM_GAIN;
+            dd[r + 1] = th.y * P25_FM_GAIN;
+            if (want_pw && R * lane + r < nv) pw += c0.x * c0.x + c0.y * c0.y;
+            if (want_pw && R * lane + r + 1 < nv) pw += c1.x * c1.x + c1.y * c1.y;
+            prev = c1;
+        }
+        sm.dA[DROWS + lane] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+        sm.dB[DROWS + lane] = make_float4(dd[4], dd[5], dd[6], dd[7]);
+        __syncwarp();                                                                 // S2
+
+        // ---- boxcar over d[o - 9 .. o], o = 8 lane + r: the row below holds d[8 lane - 8 .. 8 lane - 1]
+        {
+            const float4 o4 = sm.dB[lane], ha = sm.dA[lane + 1], hb = sm.dB[lane + 1];
+            const float old[R] = {o4.w, ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z};
+            float sum[R];
+            float s0 = old[0] + old[1];
+            s0 += old[2]; s0 += old[3]; s0 += old[4]; s0 += old[5]; s0 += old[6]; s0 += old[7]; s0 += hb.w; s0 += dd[0];
+            sum[0] = s0;
+#pragma unroll
+            for (int r = 1; r < R; r++) sum[r] = (sum[r - 1] - old[r - 1]) + dd[r];
+            const float kk = 1.0f / P25_BOXCAR;
+            const int o0 = R * lane;
+            if (o0 < nv) {
+                float* out = out_lane + NOUT * it;
+                if (o0 + R - 1 < nv) {
+                    reinterpret_cast<float4*>(out)[0] = make_float4(sum[0] * kk, sum[1] * kk, sum[2] * kk, sum[3] * kk);
+                    reinterpret_cast<float4*>(out)[1] = make_float4(sum[4] * kk, sum[5] * kk, sum[6] * kk, sum[7] * kk);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+                        if (o0 + r < nv) out[r] = sum[r] * kk;
+                }
+            }
+        }
+        // ---- roll the histories: the last 5 decimator rows of the four arrays and 2 discriminator rows move to the front
+        float4 ry = make_float4(0.f, 0.f, 0.f, 0.f), rd = ry;
+        const int yq = lane / HROWS, yr = lane - HROWS * yq;
+        if (lane < 4 * HROWS) ry = sm.yd[yq][32 + yr];
+        if (lane < 2 * DROWS) rd = (lane & 1) ? sm.dB[32 + (lane >> 1)] : sm.dA[32 + (lane >> 1)];
+        __syncwarp();                                                                 // S3
+        if (lane < 4 * HROWS) sm.yd[yq][yr] = ry;
+        if (lane < 2 * DROWS) {
+            if (lane & 1) sm.dB[lane >> 1] = rd;
+            else sm.dA[lane >> 1] = rd;
+        }
+      }
+      if (want_pw) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) pw += __shfl_xor_sync(0xFFFFFFFFu, pw, o);
+          if (lane == 0) atomicAdd(p.power_sum + s, pw * pw_scale);
+      }
+      if (it_first + n_st == ips) {
+          const uint4* src = reinterpret_cast<const uint4*>(chunk + ((size_t)p.n - p.ht) * ES);
+          uint4* dst = reinterpret_cast<uint4*>((unsigned char*)p.tail_out + s * tail_bytes);
+          for (int i = lane; i < (int)(tail_bytes / 16); i += 32) dst[i] = src[i];
+      }
+      s++;
+      it_first = 0;
+      chunk += row_bytes;
+      tail += tail_bytes;
+    }
+}
+
+// host side: the banded tap matrix in fragment order, and the accumulator start values
+struct Tables {
+    uint2 b[4][NB][32];
+    int init[3];
+    double gain;                                // sum of the quantised taps / 2^25 (DC gain of the integer decimator)
+    Tables() {
+        int limb[P25_TAPS_DECIM][3];
+        long long sum[3] = {0, 0, 0}, tsum = 0;
+        for (int k = 0; k < P25_TAPS_DECIM; k++) {
+            const long long t = llround((double)P25_TAPS_DECIM_H[k] * (double)(1 << SCALE_LOG2));
+            long long v = t;
+            for (int l = 0; l < 3; l++) {
+                const long long d = ((v + 128) & 255) - 128;    // balanced digit in [-128, 127]
+                limb[k][l] = (int)d;
+                v = (v - d) / 256;
+                sum[l] += d;
+            }
+            tsum += t;                          // v == 0 here: |t| < 2^23 for this tap set
+        }
+        gain = (double)tsum / (double)(1 << SCALE_LOG2);
+        for (int l = 0; l < 3; l++) init[l] = 0x4B400000 - 128 * (int)sum[l];
+        for (int sk = 0; sk < 4; sk++)
+            for (int nt = 0; nt < 2; nt++)
+                for (int jj = 0; jj < 3; jj++)
+                    for (int l = 0; l < 3; l++)
+                        for (int ln = 0; ln < 32; ln++) {
+                            const int n = ln >> 2, tig = ln & 3, ks = nt + jj;
+                            unsigned w[2] = {0u, 0u};
+                            for (int h = 0; h < 2; h++)
+                                for (int bb = 0; bb < 4; bb++) {
+                                    const int phi = 32 * ks + 16 * h + 4 * tig + bb;    // byte of the row window
+                                    const int smp = phi >> 1, comp = phi & 1;
+                                    const int d = smp - sk - 5 * (4 * nt + (n >> 1));
+                                    int v = 0;
+                                    if (comp == (n & 1) && d >= 0 && d < P25_TAPS_DECIM) v = limb[P25_TAPS_DECIM - 1 - d][l];
+                                    w[h] |= (unsigned)(v & 255) << (8 * bb);
+                                }
+                            b[sk][(nt * 3 + jj) * 3 + l][ln] = make_uint2(w[0], w[1]);
+                        }
+    }
+};
+static const Tables& tables() {
+    static const Tables t;
+    return t;
+}
+
+}  // namespace w5i
+
 unsigned p25cu_ddc_tail_len(int decimation) { return decimation == 50 ? Cfg<true>::HT : Cfg<false>::HT; }
 
 cudaError_t p25cu_ddc_upload_taps() {
@@ -1380,6 +1732,7 @@ cudaError_t p25cu_ddc_upload_taps() {
     if ((e = cudaMemcpyToSymbol(c_taps_front, P25_TAPS_FRONT_H, sizeof(c_taps_front))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_taps_decim, P25_TAPS_DECIM_H, sizeof(c_taps_decim))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_taps_chan, P25_TAPS_CHAN_H, sizeof(c_taps_chan))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(w5i::g_btab, w5i::tables().b, sizeof(w5i::g_btab))) != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_iq_lut, P25_IQ_LUT, sizeof(c_iq_lut));
 }
 
@@ -1455,6 +1808,22 @@ static cudaError_t launch_w5(const DdcParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+static cudaError_t launch_w5i(const DdcParams& p, cudaStream_t st) {
+    const size_t smem = sizeof(w5i::WarpSm) * w5i::WARPS + sizeof(uint2) * w5i::NB * 32;
+    const unsigned ips = (p.n_out + w5i::NOUT - 1) / w5i::NOUT;
+    const unsigned long long total = (unsigned long long)p.n_streams * ips;
+    unsigned long long want = (total + 3) / 4;                 // at least ~4 iterations per warp (one warm-up each)
+    want = (want + w5i::WARPS - 1) / w5i::WARPS;
+    const unsigned grid = want < (unsigned long long)p.plan->grid_w5i ? (unsigned)(want ? want : 1) : (unsigned)p.plan->grid_w5i;
+    const w5i::Tables& t = w5i::tables();
+    // yd is in byte units x 2^25: the half LSB of the u8 mapping enters the channel filter at that scale
+    const double sc = (double)(1 << w5i::SCALE_LOG2);
+    const float dc = (float)(0.5 * t.gain * tap_gain(P25_TAPS_CHAN_H, P25_TAPS_CHAN) * sc);
+    const float pw_scale = (float)(1.0 / (127.5 * 127.5) / (sc * sc));
+    w5i::p25_ddc5_imma_kernel<<<grid, 32 * w5i::WARPS, smem, st>>>(p, ips, dc, pw_scale, t.init[0], t.init[1], t.init[2]);
+    return cudaGetLastError();
+}
+
 // Per-device setup (called once per device under the library's plan mutex, with that device current): opt every
 // kernel into its dynamic shared memory and size the persistent grids from the device's own occupancy.
 template <typename K>
@@ -1486,6 +1855,11 @@ cudaError_t p25cu_ddc_plan_device(P25DevPlan* plan) {
         const int per_sm = atoi(ev);
         if (per_sm > 0) plan->grid_w5[U8] = plan->grid_w5[CF] = n_sm * per_sm;
     }
+    if ((e = plan_one(w5i::p25_ddc5_imma_kernel, 32 * w5i::WARPS, sizeof(w5i::WarpSm) * w5i::WARPS + sizeof(uint2) * w5i::NB * 32, n_sm, &plan->grid_w5i)) != cudaSuccess) return e;
+    if (const char* ev = getenv("P25CU_W5_CTAS")) {
+        const int per_sm = atoi(ev);
+        if (per_sm > 0) plan->grid_w5i = n_sm * per_sm;
+    }
     const size_t atab = w5::ATAB_FLOATS * sizeof(float);
     if ((e = plan_one(w5::p25_ddc5_warp_kernel<U8, true>, 32 * w5::WARPS, sizeof(w5::WarpSm<U8, true>) * w5::WARPS + atab, n_sm, &plan->grid_w5m[U8])) != cudaSuccess) return e;
     if ((e = plan_one(w5::p25_ddc5_warp_kernel<CF, true>, 32 * w5::WARPS, sizeof(w5::WarpSm<CF, true>) * w5::WARPS + atab, n_sm, &plan->grid_w5m[CF])) != cudaSuccess) return e;
@@ -1497,7 +1871,7 @@ cudaError_t p25cu_ddc_plan_device(P25DevPlan* plan) {
 }
 
 // /5 fast paths: bit 0 = warp-autonomous kernel for u8, bit 1 = for cf32 (otherwise the tile kernel), bit 2 = its channel
-// filter on the tensor pipe; A/B switch P25CU_DDC5
+// filter on the tensor pipe, bit 3 = u8 warp kernel with the decimator on the integer tensor pipe; A/B switch P25CU_DDC5
 static int ddc5_variant() {
     static const int v = getenv("P25CU_DDC5") ? atoi(getenv("P25CU_DDC5")) : 3;
     return v;
@@ -1507,6 +1881,7 @@ cudaError_t p25cu_launch_ddc(const DdcParams& p, int format, int decimation, cud
     if (p.n_out == 0 && p.n == 0) return cudaSuccess;
     if (decimation == 5 && p.aligned16 && p.n_out > 0 && p.a0 >= p.ht && p.n >= p.ht && p.ht == (unsigned)Cfg<false>::HT) {
         const bool mma = (ddc5_variant() & 4) != 0;     // channel filter on the tensor pipe (mma.sync 3xTF32)
+        if (format == P25CU_FMT_U8_IQ && (ddc5_variant() & 8)) return launch_w5i(p, st);   // decimator on the integer tensor pipe
         if (format == P25CU_FMT_U8_IQ && (ddc5_variant() & 1))
             return mma ? launch_w5<P25CU_FMT_U8_IQ, true>(p, st) : launch_w5<P25CU_FMT_U8_IQ, false>(p, st);
         if (format == P25CU_FMT_CF32_IQ && (ddc5_variant() & 2))

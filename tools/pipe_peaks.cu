@@ -210,6 +210,86 @@ __global__ void __launch_bounds__(256) k_prmt_plus_ffma2(float* out, unsigned w,
     if (s == 12345.678f) out[0] = s;
 }
 
+// legacy integer tensor pipe: mma.sync m16n8k32 u8 x s8 -> s32 (the /5 decimator on raw IQ bytes)
+__global__ void __launch_bounds__(256) k_imma(int* out, unsigned a, unsigned b) {
+    int d[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) d[i][j] = 0;
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+r"(d[i][0]), "+r"(d[i][1]), "+r"(d[i][2]), "+r"(d[i][3])
+                         : "r"(a), "r"(a + 1), "r"(a + 2), "r"(a + 3), "r"(b), "r"(b + 1));
+    }
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) s += d[i][j];
+    if (s == 123456789) out[0] = s;
+}
+
+// the mix of the IMMA decimator kernel: 1 IMMA per 12 FFMA2 (two IMMA chains, 24 FFMA2 per round)
+__global__ void __launch_bounds__(256) k_imma_plus_ffma2(float* out, unsigned a, unsigned b, float fa, float fb) {
+    int d[2][4];
+    unsigned long long acc[CHAINS];
+    const float2 aa = make_float2(fa, fa), bb = make_float2(fb, fb);
+    const unsigned long long A = *reinterpret_cast<const unsigned long long*>(&aa), B = *reinterpret_cast<const unsigned long long*>(&bb);
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) d[i][j] = 0;
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) {
+        const float2 v = make_float2(threadIdx.x * 1e-3f + i, 1.f);
+        acc[i] = *reinterpret_cast<const unsigned long long*>(&v);
+    }
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+r"(d[i][0]), "+r"(d[i][1]), "+r"(d[i][2]), "+r"(d[i][3])
+                         : "r"(a), "r"(a + 1), "r"(a + 2), "r"(a + 3), "r"(b), "r"(b + 1));
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int i = 0; i < CHAINS; i++) acc[i] = fma2(acc[i], A, B);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) s += (float)d[i][j];
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) {
+        const float2 v = *reinterpret_cast<float2*>(&acc[i]);
+        s += v.x + v.y;
+    }
+    if (s == 12345.678f) out[0] = s;
+}
+
+// int -> float conversions (I2F) per clock: one way to turn the IMMA accumulators into floats
+__global__ void __launch_bounds__(256) k_i2f(float* out, int a) {
+    int v[CHAINS];
+    float f[CHAINS];
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) { v[i] = a + threadIdx.x + i; f[i] = 0.f; }
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < CHAINS; i++) {
+            f[i] = __int2float_rn(v[i]);
+            v[i] = __float_as_int(f[i]) ^ it;
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) s += f[i];
+    if (s == 12345.678f) out[0] = s;
+}
+
 template <typename F>
 static double time_ms(F launch, int reps = 5) {
     cudaEvent_t e0, e1;
@@ -247,6 +327,9 @@ int main() {
     const double t_both = time_ms([&] { k_mma_plus_ffma2<<<grid, block>>>(d_out, 0x3f800000u, 0x3f000000u, 1.0001f, 0.5f); });
     const double t_dp4a = time_ms([&] { k_dp4a<<<grid, block>>>((int*)d_out, 0x01020304, 0x01010101); });
     const double t_prmt = time_ms([&] { k_prmt_plus_ffma2<<<grid, block>>>(d_out, 0x12345678u, 1.0001f, 0.5f); });
+    const double t_imma = time_ms([&] { k_imma<<<grid, block>>>((int*)d_out, 0x01020304u, 0x01010101u); });
+    const double t_imma_both = time_ms([&] { k_imma_plus_ffma2<<<grid, block>>>(d_out, 0x01020304u, 0x01010101u, 1.0001f, 0.5f); });
+    const double t_i2f = time_ms([&] { k_i2f<<<grid, block>>>(d_out, 12345); });
     CK(cudaGetLastError());
     const double fma_ffma = threads * ITERS * CHAINS / (t_ffma * 1e-3);            // FMA / s
     const double fma_ffma2 = threads * ITERS * CHAINS * 2 / (t_ffma2 * 1e-3);
@@ -258,6 +341,10 @@ int main() {
     const double both_fma = threads * ITERS * 2 * CHAINS * 2 / (t_both * 1e-3);
     const double dp4a = threads * ITERS * CHAINS * 4 / (t_dp4a * 1e-3);
     const double prmt_fma = threads * ITERS * CHAINS * 2 / (t_prmt * 1e-3);
+    const double mac_imma = warps * ITERS * 4 * (16.0 * 8 * 32) / (t_imma * 1e-3);
+    const double imma_both_mac = warps * ITERS * 2 * (16.0 * 8 * 32) / (t_imma_both * 1e-3);
+    const double imma_both_fma = threads * ITERS * 3 * CHAINS * 2 / (t_imma_both * 1e-3);
+    const double i2f_rate = threads * ITERS * CHAINS / (t_i2f * 1e-3);
 
     // pinned host -> device copy ceiling (what bounds bench.py's e2e leg), 1 GiB x 5, best
     size_t bytes = (size_t)1 << 30;
@@ -277,10 +364,14 @@ int main() {
            "\"mma_sync_tf32_mac_per_clk_per_sm\": %.1f, "
            "\"concurrent_tf32_tflops\": %.1f, \"concurrent_ffma2_tflops\": %.2f, "
            "\"dp4a_tops\": %.1f, \"ffma2_tflops_with_1_prmt_each\": %.2f, "
+           "\"mma_sync_u8s8_k32_tops\": %.1f, \"mma_sync_u8s8_instr_clk_per_subcore\": %.2f, "
+           "\"concurrent_imma_tops\": %.1f, \"concurrent_imma_ffma2_tflops\": %.2f, \"i2f_per_clk_per_sm\": %.1f, "
            "\"h2d_pinned_gbs\": %.1f, \"d2h_pinned_gbs\": %.1f, "
            "\"how\": \"%d CTAs x 256 threads, %d iterations x %d independent chains per thread, best of 5, CUDA events; flops = 2 x FMA\"}\n",
            n_sm, clk, 2 * fma_ffma / 1e12, 2 * fma_ffma2 / 1e12, 2 * fma_mix / 1e12, fma_ffma / n_sm / (clk * 1e3),
            fma_ffma2 / n_sm / (clk * 1e3), 2 * mac_tf32 / 1e12, 2 * mac_bf16 / 1e12, mac_tf32 / n_sm / (clk * 1e3),
-           2 * both_mac / 1e12, 2 * both_fma / 1e12, 2 * dp4a / 1e12, 2 * prmt_fma / 1e12, h2d, d2h, grid, ITERS, CHAINS);
+           2 * both_mac / 1e12, 2 * both_fma / 1e12, 2 * dp4a / 1e12, 2 * prmt_fma / 1e12,
+           2 * mac_imma / 1e12, (clk * 1e3) * n_sm * 4 / (mac_imma / (16.0 * 8 * 32)), 2 * imma_both_mac / 1e12, 2 * imma_both_fma / 1e12,
+           i2f_rate / n_sm / (clk * 1e3), h2d, d2h, grid, ITERS, CHAINS);
     return 0;
 }
