@@ -1435,6 +1435,7 @@ struct __align__(128) WarpSm {
 };
 
 __device__ uint2 g_btab[4][NB][32];             // [sk][fragment][lane] = (b0, b1)
+__device__ int4 g_init[3];                      // accumulator start value of every limb, four times (one C operand quad)
 
 __device__ __forceinline__ void imma(int (&d)[4], const unsigned (&a)[4], const uint2 b) {
     asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -1442,10 +1443,10 @@ __device__ __forceinline__ void imma(int (&d)[4], const unsigned (&a)[4], const 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
 // first k-step of a chain: the start value (one register for all four accumulators) is the C operand
-__device__ __forceinline__ void imma0(int (&d)[4], const unsigned (&a)[4], const uint2 b, const int c) {
-    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+__device__ __forceinline__ void imma0(int (&d)[4], const unsigned (&a)[4], const uint2 b, const int (&c)[4]) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
         : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y), "r"(c));
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
 }
 // 4-byte shared-memory load the compiler may not fuse with its neighbour (an 8-byte load would need four moves to put
 // the words into the fragment's register order)
@@ -1472,9 +1473,9 @@ __device__ __forceinline__ void issue_slice(WarpSm& sm, int stage, int ht, int l
     if (nc) tma_load_1d(&sm.xs[stage][nt * ES], chunk, nc * ES, &sm.full[stage]);
 }
 
+template <bool PW>                              // PW: accumulate the channel power (every fourth chunk in the reference's cadence)
 __global__ void __launch_bounds__(32 * WARPS, MINB) p25_ddc5_imma_kernel(const DdcParams p, const unsigned its_per_stream,
-                                                                         const float dc, const float pw_scale,
-                                                                         const int init0, const int init1, const int init2) {
+                                                                         const float dc, const float pw_scale) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpSm& sm = reinterpret_cast<WarpSm*>(smem_raw)[warp];
@@ -1497,7 +1498,6 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) p25_ddc5_imma_kernel(const D
     const unsigned long long b0 = total * gw / GW, b1 = total * (gw + 1ull) / GW;
     if (b0 >= b1) return;
     const size_t row_bytes = (size_t)p.n * ES, tail_bytes = (size_t)p.ht * ES;
-    const bool want_pw = p.power_sum != nullptr;
     unsigned s = (unsigned)(b0 / its_per_stream);
     int it_first = (int)(b0 % its_per_stream);
     unsigned left = (unsigned)(b1 - b0);
@@ -1518,6 +1518,14 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) p25_ddc5_imma_kernel(const D
     const float2 unmagic = make_float2(-12582912.f, -12582912.f);
     float2 c_carry = make_float2(0.f, 0.f);
     unsigned use = 0;
+    // the three start values as register quads that stay resident (opaque to the compiler, which otherwise rebuilds a
+    // quad with four moves in front of every chain: 41 MOV per iteration)
+    int init[3][4];
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+        const int4 v = g_init[l];
+        init[l][0] = v.x; init[l][1] = v.y; init[l][2] = v.z; init[l][3] = v.w;
+    }
 
     while (left) {
       const int n_st = min(ips - it_first, (int)left);
@@ -1534,7 +1542,6 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) p25_ddc5_imma_kernel(const D
         // ---- /5 decimator on the integer tensor pipe: 36 IMMA, every B fragment loaded once for both m-tiles
         {
             int acc[2][2][3][4];
-            const int init[3] = {init0, init1, init2};
             const unsigned xa = fast::smem_u32(sm.xs[stage]) + a_off;
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
@@ -1616,8 +1623,8 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) p25_ddc5_imma_kernel(const D
             const float2 th = disc_atan2_pair(im, re);
             dd[r] = th.x * P25_FM_GAIN;
             dd[r + 1] = th.y * P25_FM_GAIN;
-            if (want_pw && R * lane + r < nv) pw += c0.x * c0.x + c0.y * c0.y;
-            if (want_pw && R * lane + r + 1 < nv) pw += c1.x * c1.x + c1.y * c1.y;
+            if (PW && R * lane + r < nv) pw += c0.x * c0.x + c0.y * c0.y;
+            if (PW && R * lane + r + 1 < nv) pw += c1.x * c1.x + c1.y * c1.y;
             prev = c1;
         }
         sm.dA[DROWS + lane] = make_float4(dd[0], dd[1], dd[2], dd[3]);
@@ -1660,7 +1667,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) p25_ddc5_imma_kernel(const D
             else sm.dA[lane >> 1] = rd;
         }
       }
-      if (want_pw) {
+      if constexpr (PW) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) pw += __shfl_xor_sync(0xFFFFFFFFu, pw, o);
           if (lane == 0) atomicAdd(p.power_sum + s, pw * pw_scale);
@@ -1733,6 +1740,12 @@ cudaError_t p25cu_ddc_upload_taps() {
     if ((e = cudaMemcpyToSymbol(c_taps_decim, P25_TAPS_DECIM_H, sizeof(c_taps_decim))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_taps_chan, P25_TAPS_CHAN_H, sizeof(c_taps_chan))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(w5i::g_btab, w5i::tables().b, sizeof(w5i::g_btab))) != cudaSuccess) return e;
+    {
+        const w5i::Tables& t = w5i::tables();
+        const int4 q[3] = {make_int4(t.init[0], t.init[0], t.init[0], t.init[0]), make_int4(t.init[1], t.init[1], t.init[1], t.init[1]),
+                           make_int4(t.init[2], t.init[2], t.init[2], t.init[2])};
+        if ((e = cudaMemcpyToSymbol(w5i::g_init, q, sizeof(q))) != cudaSuccess) return e;
+    }
     return cudaMemcpyToSymbol(c_iq_lut, P25_IQ_LUT, sizeof(c_iq_lut));
 }
 
@@ -1820,7 +1833,8 @@ static cudaError_t launch_w5i(const DdcParams& p, cudaStream_t st) {
     const double sc = (double)(1 << w5i::SCALE_LOG2);
     const float dc = (float)(0.5 * t.gain * tap_gain(P25_TAPS_CHAN_H, P25_TAPS_CHAN) * sc);
     const float pw_scale = (float)(1.0 / (127.5 * 127.5) / (sc * sc));
-    w5i::p25_ddc5_imma_kernel<<<grid, 32 * w5i::WARPS, smem, st>>>(p, ips, dc, pw_scale, t.init[0], t.init[1], t.init[2]);
+    if (p.power_sum) w5i::p25_ddc5_imma_kernel<true><<<grid, 32 * w5i::WARPS, smem, st>>>(p, ips, dc, pw_scale);
+    else w5i::p25_ddc5_imma_kernel<false><<<grid, 32 * w5i::WARPS, smem, st>>>(p, ips, dc, pw_scale);
     return cudaGetLastError();
 }
 
@@ -1855,7 +1869,9 @@ cudaError_t p25cu_ddc_plan_device(P25DevPlan* plan) {
         const int per_sm = atoi(ev);
         if (per_sm > 0) plan->grid_w5[U8] = plan->grid_w5[CF] = n_sm * per_sm;
     }
-    if ((e = plan_one(w5i::p25_ddc5_imma_kernel, 32 * w5i::WARPS, sizeof(w5i::WarpSm) * w5i::WARPS + sizeof(uint2) * w5i::NB * 32, n_sm, &plan->grid_w5i)) != cudaSuccess) return e;
+    const size_t smem_w5i = sizeof(w5i::WarpSm) * w5i::WARPS + sizeof(uint2) * w5i::NB * 32;
+    if ((e = plan_one(w5i::p25_ddc5_imma_kernel<true>, 32 * w5i::WARPS, smem_w5i, n_sm, &plan->grid_w5i)) != cudaSuccess) return e;
+    if ((e = plan_one(w5i::p25_ddc5_imma_kernel<false>, 32 * w5i::WARPS, smem_w5i, n_sm, &plan->grid_w5i)) != cudaSuccess) return e;
     if (const char* ev = getenv("P25CU_W5_CTAS")) {
         const int per_sm = atoi(ev);
         if (per_sm > 0) plan->grid_w5i = n_sm * per_sm;
@@ -1873,7 +1889,7 @@ cudaError_t p25cu_ddc_plan_device(P25DevPlan* plan) {
 // /5 fast paths: bit 0 = warp-autonomous kernel for u8, bit 1 = for cf32 (otherwise the tile kernel), bit 2 = its channel
 // filter on the tensor pipe, bit 3 = u8 warp kernel with the decimator on the integer tensor pipe; A/B switch P25CU_DDC5
 static int ddc5_variant() {
-    static const int v = getenv("P25CU_DDC5") ? atoi(getenv("P25CU_DDC5")) : 3;
+    static const int v = getenv("P25CU_DDC5") ? atoi(getenv("P25CU_DDC5")) : 11;
     return v;
 }
 
