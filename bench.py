@@ -76,13 +76,13 @@ class Workload:
         if name == "cfg5":
             assert 65536 % world == 0
             self.streams, self.fs, self.decim, self.fmt, self.scaling = 65536 // world, 240_000, 5, "u8", "strong"
-            self.kernel = "w5::p25_ddc5_warp_kernel<u8> (/5)"
+            self.kernel = "w5i::p25_ddc5_imma_kernel (u8 /5: decimator on the integer tensor pipe, channel filter on FFMA2)"
             self.desc = ("configs[4]: 65,536 synthetic P25 control-channel streams in the reference's own format (u8 IQ, 240 kS/s, "
                          f"/5 -> 48 kHz), {self.streams} per GPU, 36000 samples (150 ms) per stream per step")
         elif name == "cfg4":
             self.streams, self.fs, self.decim, self.fmt, self.scaling = 16384, 240_000, 5, "u8", "weak"
             self.kind, self.snr = "traffic", 12.0
-            self.kernel = "w5::p25_ddc5_warp_kernel<u8> (/5)"
+            self.kernel = "w5i::p25_ddc5_imma_kernel (u8 /5: decimator on the integer tensor pipe, channel filter on FFMA2)"
             self.desc = ("configs[3]: 16,384 voice traffic channels per GPU (HDU, LDU1/LDU2 with IMBE frames, TDULC) at 12 dB with "
                          "carrier offset, u8 IQ 240 kS/s, one superframe per stream per step")
         elif name == "cfg1":
@@ -227,6 +227,14 @@ def measured_peaks():
     except Exception:
         pass
     return hbm, src, fp32
+
+
+def pipe_peak(key: str):
+    try:
+        with open(os.path.join(ROOT, "profiles", "pipe_peaks_r02.json")) as f:
+            return float(json.load(f)[key])
+    except Exception:
+        return None
 
 
 class StreamGate:
@@ -598,7 +606,7 @@ def summarise(wl: Workload, m: dict, world: int, K: int, hbm: float, hbm_src: st
     achieved = alg / (m["ddc_ms"] * 1e-3) / 1e9
     roof = {"kernel": wl.kernel, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
             "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": m["ddc_ms"]}
-    tf = {"cfg2": "ddc_fm_traffic.json", "cfg5": "ddc5_u8_traffic.json", "cfg3": "pfb_traffic.json"}.get(wl.name)
+    tf = {"cfg2": "ddc_fm_traffic.json", "cfg5": "ddc5_u8_imma_traffic.json", "cfg3": "pfb_traffic.json"}.get(wl.name)
     if tf:
         try:
             with open(os.path.join(ROOT, "profiles", tf)) as f:
@@ -610,6 +618,12 @@ def summarise(wl: Workload, m: dict, world: int, K: int, hbm: float, hbm_src: st
     if wl.decim == 5 or wl.fmt == "u8" or wl.kind == "wide":
         # FP32-bound shapes: FIR FMAs per 48 kHz output against the measured FFMA2 peak
         fma = {5: 2 * (25 + 41), 50: 2 * (250 + 25 + 41), 400: 2 * 15 + 26}[wl.decim]   # FMAs per 48 kHz output
+        if wl.decim == 5 and wl.fmt == "u8":
+            # the /5 decimator of the u8 kernel runs as u8 x s8 mma.sync (36 x m16n8k32 per 256 outputs, issued ops incl. the
+            # zeros of the band); only the 41-tap channel filter is left on the FP32 pipe
+            fma = 2 * 41
+            roof["tensor_int8_tops"] = 2.0 * 36 * 16 * 8 * 32 / 256 * wl.streams * (n // wl.decim) / (m["ddc_ms"] * 1e-3) / 1e12
+            roof["tensor_int8_peak_tops"] = pipe_peak("mma_sync_u8s8_k32_tops")   # legacy mma.sync rate, tools/pipe_peaks.cu
         flops = 2.0 * fma * wl.streams * (n // wl.decim)
         roof["fp32_tflops"] = flops / (m["ddc_ms"] * 1e-3) / 1e12
         if fp32:
