@@ -1732,6 +1732,340 @@ static const Tables& tables() {
 
 }  // namespace w5i
 
+
+// =====================================================================================================
+// u8 at 2.4 MS/s (/50) with BOTH decimating stages on the integer tensor pipe (round 2).  The /10 front stage and the /5
+// decimator are linear and see nothing but bytes in front of them, so their cascade is ONE 290-tap FIR at 2.4 MS/s,
+// g[10 k + i] = hd[k] hf[i], decimating by 50 straight to the 48 kHz decimator output -- 290 exact integer MACs per
+// output and component instead of 250 + 21 FFMA2 (the stream kernel above is FP32-bound: 30 % of the FFMA2 peak at 28 %
+// of HBM).  Same scheme as w5i: raw bytes as the A operand (sixteen overlapping rows of the TMA-staged slice, 200 samples
+// = 400 bytes apart, four outputs per row = one n-tile), the taps as a banded s8 matrix in three balanced limbs of
+// t = round(g 2^28), accumulators started at the bit pattern of 1.5 * 2^23 - 128 * (limb sum) so that they are floats,
+// y = 2^16 s2 + 2^8 s1 + s0 in one FADD2 per limb + two FFMA2.  28 k-steps x 3 limbs = 84 IMMA per 64 outputs; every B
+// fragment (21.5 KB table per CTA) is loaded once for the two m-tiles of a 128-output warp iteration.  The row stride of
+// 100 words puts the 32 lanes of every fragment load on 32 different banks; the four outputs of a row are one row of
+// the channel filter's window arrays.  The 48 kHz stages are the warp kernel's (4 outputs per lane).
+// The warm-up iteration of a piece that starts a chunk reaches 6,640 samples back but only its last 50 outputs (2,740
+// samples, inside the 3,264-sample tail) have to be right: bytes in front of the tail are simply not copied, and whatever
+// lies in the buffer gives finite garbage in outputs nobody keeps.
+// =====================================================================================================
+namespace w50i {
+
+using fast::mbar_init;
+using fast::mbar_expect_tx;
+using fast::mbar_wait;
+using fast::tma_load_1d;
+using fast::cfma;
+using fast5::add2;
+using fast5::disc_atan2_pair;
+using w5i::imma;
+using w5i::imma0;
+using w5i::lds32;
+
+constexpr int D = 50;
+constexpr int G = P25_TAPS_FRONT + P25_DECIM_FRONT * (P25_TAPS_DECIM - 1);   // 290 combined taps
+constexpr int R = 4;
+constexpr int NOUT = 32 * R;                            // 128 outputs per warp iteration: two m-tiles of 16 rows x 4 outputs
+constexpr int XNEW = D * NOUT;                          // 6400 fresh input samples per iteration
+constexpr int XREAD = D * (NOUT - 1) + G;               // 6640 samples read
+constexpr int WARPS = 6;                                // one CTA per SM: 6 x 28 KB of slices + the B table
+constexpr int AL = 8, ES = 2;
+constexpr int XLEN = (XREAD + 2 * AL - 2) / AL * AL;    // 6648
+constexpr int KS = 28;                                  // k-steps: 1 + 150 + 290 = 441 samples <= 448
+constexpr int XBYTES = (400 * 31 + 12 + 32 * KS + 127) / 128 * 128;   // 13312: every A load stays inside the stage buffer
+constexpr int HROWS = (P25_TAPS_CHAN - 1) / R;          // 10
+constexpr int DROWS = 3;
+constexpr int NB = KS * 3;                              // B fragments: [k-step][limb]
+constexpr int SCALE_LOG2 = 28;                          // taps as round(g * 2^28): |t| < 2^23
+static_assert(XBYTES >= XLEN * ES && XNEW % (2 * AL) == 0 && 1 + D * 3 + G <= 16 * KS, "slice, constant skew, window");
+static_assert((P25_TAPS_CHAN - 1) % R == 0 && DROWS * R >= P25_BOXCAR - 1, "history rows");
+
+struct __align__(128) WarpSm {
+    unsigned char xs[2][XBYTES];
+    float4 ydA[HROWS + 32 + 2];                 // 44 rows: ydB starts 16 banks further (half-warp stores: 32 banks)
+    float4 ydB[HROWS + 32];
+    float4 d4[DROWS + 32];
+    unsigned long long full[2];
+};
+
+__device__ uint2 g_btab[2][NB][32];             // [skew & 1][fragment][lane]
+__device__ int4 g_init[3];
+
+// bulk copy of the slice whose first input has logical index l0 (tail ++ chunk); the part in front of the tail
+// (l0 < 0: warm-up of a chunk's first piece) is skipped, the destination keeps its offset
+__device__ __forceinline__ void issue_slice(WarpSm& sm, int stage, int ht, int lend, const unsigned char* tail,
+                                            const unsigned char* chunk, int l0) {
+    const int la0 = l0 & ~(AL - 1);
+    const int la = max(la0, 0);
+    const int lb = min(la0 + XLEN, lend);
+    unsigned char* dst = &sm.xs[stage][(la - la0) * ES];
+    if (la >= ht) {
+        const unsigned bytes = (unsigned)(lb - la) * ES;
+        mbar_expect_tx(&sm.full[stage], bytes);
+        tma_load_1d(dst, chunk + (size_t)(la - ht) * ES, bytes, &sm.full[stage]);
+        return;
+    }
+    const int t1 = min(lb, ht);
+    const unsigned nt = (unsigned)(t1 - la), nc = (unsigned)(lb - t1);
+    mbar_expect_tx(&sm.full[stage], (nt + nc) * ES);
+    tma_load_1d(dst, tail + (size_t)la * ES, nt * ES, &sm.full[stage]);
+    if (nc) tma_load_1d(dst + nt * ES, chunk, nc * ES, &sm.full[stage]);
+}
+
+template <bool PW>
+__global__ void __launch_bounds__(32 * WARPS, 1) p25_ddc50_imma_kernel(const DdcParams p, const unsigned its_per_stream,
+                                                                       const float dc, const float pw_scale) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSm& sm = reinterpret_cast<WarpSm*>(smem_raw)[warp];
+    uint2* const btab = reinterpret_cast<uint2*>(smem_raw + sizeof(WarpSm) * WARPS);
+    const int ips = (int)its_per_stream, ht = (int)p.ht, lend = (int)p.ht + (int)p.n, n_out = (int)p.n_out;
+    // logical index (tail ++ chunk) of the first input of iteration 0's window: output m uses 50 m + lbase + [-240, 49]
+    const int l_base = (int)(D * (long long)p.m0 - (long long)p.a0) - (G - D) + ht;
+    const int skew = l_base & (AL - 1);                     // the same for every iteration of every stream
+    for (int e = threadIdx.x; e < NB * 32; e += 32 * WARPS) btab[e] = (&g_btab[skew & 1][0][0])[e];
+    if (lane == 0) {
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = lane; i < 2 * XBYTES / 16; i += 32) reinterpret_cast<uint4*>(sm.xs)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = lane; i < HROWS + 32; i += 32) sm.ydA[i] = sm.ydB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < DROWS + 32; i += 32) sm.d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zeroed stage buffers are overwritten by bulk copies
+    __syncthreads();
+
+    const unsigned gw = blockIdx.x * WARPS + warp, GW = gridDim.x * WARPS;
+    const unsigned long long total = (unsigned long long)p.n_streams * its_per_stream;
+    const unsigned long long b0 = total * gw / GW, b1 = total * (gw + 1ull) / GW;
+    if (b0 >= b1) return;
+    const size_t row_bytes = (size_t)p.n * ES, tail_bytes = (size_t)p.ht * ES;
+    unsigned s = (unsigned)(b0 / its_per_stream);
+    int it_first = (int)(b0 % its_per_stream);
+    unsigned left = (unsigned)(b1 - b0);
+    const unsigned char* chunk = (const unsigned char*)p.iq + s * row_bytes;
+    const unsigned char* tail = (const unsigned char*)p.tail_in + s * tail_bytes;
+    if (lane == 0) {
+        issue_slice(sm, 0, ht, lend, tail, chunk, l_base + XNEW * (it_first - 1));
+        issue_slice(sm, 1, ht, lend, tail, chunk, l_base + XNEW * it_first);
+    }
+    // fragment geometry: mma rows g and g + 8 of m-tile mt read slice rows 16 mt + g and + 8 (400 bytes apart); the
+    // lane's words of a k-step are t and t + 4 of its eight; (c0, c1) / (c2, c3) are output 4 row + t
+    const int g = lane >> 2, tig = lane & 3;
+    const unsigned a_off = 400u * g + 4u * (skew >> 1) + 4u * tig;
+    const uint2* const bl = btab + lane;
+    float2* const ydst = reinterpret_cast<float2*>(tig < 2 ? &sm.ydA[HROWS + g] : &sm.ydB[HROWS + g]) + (tig & 1);
+    const float2 unmagic = make_float2(-12582912.f, -12582912.f);
+    float2 c_carry = make_float2(0.f, 0.f);
+    unsigned use = 0;
+    int init[3][4];
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+        const int4 v = g_init[l];
+        init[l][0] = v.x; init[l][1] = v.y; init[l][2] = v.z; init[l][3] = v.w;
+    }
+
+    while (left) {
+      const int n_st = min(ips - it_first, (int)left);
+      const int npiece = n_st + 1;
+      left -= (unsigned)n_st;
+      float* const out_lane = p.bb + (size_t)s * p.row_stride + P25CU_BB_HIST + R * lane;
+      float pw = 0.f;
+      for (int j = 0; j < npiece; j++, use++) {
+        const int it = it_first - 1 + j;
+        const int stage = use & 1;
+        const int nv = j ? min(n_out - NOUT * it, NOUT) : 0;
+        mbar_wait(&sm.full[stage], (use >> 1) & 1);
+
+        // ---- /50: 290-tap FIR on the raw bytes, 168 IMMA
+        {
+            int acc[2][3][4];
+            const unsigned xa = fast::smem_u32(sm.xs[stage]) + a_off;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                unsigned a[2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    const unsigned ad = xa + 6400u * mt + 32u * ks;
+                    a[mt][0] = lds32(ad);
+                    a[mt][1] = lds32(ad + 3200u);
+                    a[mt][2] = lds32(ad + 16u);
+                    a[mt][3] = lds32(ad + 3216u);
+                }
+#pragma unroll
+                for (int l = 0; l < 3; l++) {
+                    const uint2 b = bl[32 * (ks * 3 + l)];
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        if (ks == 0) imma0(acc[mt][l], a[mt], b, init[l]);
+                        else imma(acc[mt][l], a[mt], b);
+                    }
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    float2 f[3];
+#pragma unroll
+                    for (int l = 0; l < 3; l++)
+                        f[l] = add2(make_float2(__int_as_float(acc[mt][l][2 * h]), __int_as_float(acc[mt][l][2 * h + 1])), unmagic);
+                    ydst[2 * (16 * mt + 8 * h)] = cfma(65536.f, f[2], cfma(256.f, f[1], f[0]));
+                }
+        }
+        __syncwarp();                                                                 // S1: xs[stage] consumed, rows visible
+        if (lane == 0) {
+            if (j + 2 < npiece) issue_slice(sm, stage, ht, lend, tail, chunk, l_base + XNEW * (it + 2));
+            else if (left) issue_slice(sm, stage, ht, lend, tail + tail_bytes, chunk + row_bytes, l_base + XNEW * (j + 1 - npiece));
+        }
+
+        // ---- channel-select FIR: outputs 4 lane + r, window = rows lane .. lane + 10 (44 samples, s = 40 + r - k)
+        float2 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = make_float2(dc, dc);
+#pragma unroll
+        for (int t = 0; t <= HROWS; t++) {
+            const float4 va = sm.ydA[lane + t], vb = sm.ydB[lane + t];
+            const float2 xs4[4] = {make_float2(va.x, va.y), make_float2(va.z, va.w), make_float2(vb.x, vb.y), make_float2(vb.z, vb.w)};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int k = (P25_TAPS_CHAN - 1) + r - (4 * t + q);
+                    if (k >= 0 && k < P25_TAPS_CHAN) acc[r] = cfma(c_taps_chan[k], xs4[q], acc[r]);
+                }
+            }
+        }
+        // ---- FM discriminator
+        float2 prev;
+        prev.x = __shfl_up_sync(0xFFFFFFFFu, acc[R - 1].x, 1);
+        prev.y = __shfl_up_sync(0xFFFFFFFFu, acc[R - 1].y, 1);
+        if (lane == 0) prev = c_carry;
+        c_carry.x = __shfl_sync(0xFFFFFFFFu, acc[R - 1].x, 31);
+        c_carry.y = __shfl_sync(0xFFFFFFFFu, acc[R - 1].y, 31);
+        float dd[R];
+#pragma unroll
+        for (int r = 0; r < R; r += 2) {
+            const float2 c0 = acc[r], c1 = acc[r + 1];
+            const float2 re = make_float2(c0.x * prev.x + c0.y * prev.y, c1.x * c0.x + c1.y * c0.y);
+            const float2 im = make_float2(c0.y * prev.x - c0.x * prev.y, c1.y * c0.x - c1.x * c0.y);
+            const float2 th = disc_atan2_pair(im, re);
+            dd[r] = th.x * P25_FM_GAIN;
+            dd[r + 1] = th.y * P25_FM_GAIN;
+            if (PW && R * lane + r < nv) pw += c0.x * c0.x + c0.y * c0.y;
+            if (PW && R * lane + r + 1 < nv) pw += c1.x * c1.x + c1.y * c1.y;
+            prev = c1;
+        }
+        sm.d4[DROWS + lane] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+        __syncwarp();                                                                 // S2
+
+        // ---- boxcar over d[o - 9 .. o], o = 4 lane + r: rows lane .. lane + 2 hold d[4 lane - 12 .. 4 lane - 1]
+        {
+            const float4 a4 = sm.d4[lane], b = sm.d4[lane + 1], c4 = sm.d4[lane + 2];
+            const float a = a4.w;
+            float s0 = a + b.x;
+            s0 += b.y; s0 += b.z; s0 += b.w; s0 += c4.x; s0 += c4.y; s0 += c4.z; s0 += c4.w; s0 += dd[0];
+            const float s1 = (s0 - a) + dd[1], s2 = (s1 - b.x) + dd[2], s3 = (s2 - b.y) + dd[3];
+            const float kk = 1.0f / P25_BOXCAR;
+            const int o0 = R * lane;
+            if (o0 < nv) {
+                float* out = out_lane + NOUT * it;
+                if (o0 + 3 < nv) *reinterpret_cast<float4*>(out) = make_float4(s0 * kk, s1 * kk, s2 * kk, s3 * kk);
+                else {
+                    out[0] = s0 * kk;
+                    if (o0 + 1 < nv) out[1] = s1 * kk;
+                    if (o0 + 2 < nv) out[2] = s2 * kk;
+                }
+            }
+        }
+        // ---- roll the histories: the last 10 decimator rows and 3 discriminator rows move to the front
+        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra, rd = ra;
+        if (lane < HROWS) {
+            ra = sm.ydA[32 + lane];
+            rb = sm.ydB[32 + lane];
+        }
+        if (lane < DROWS) rd = sm.d4[32 + lane];
+        __syncwarp();                                                                 // S3
+        if (lane < HROWS) {
+            sm.ydA[lane] = ra;
+            sm.ydB[lane] = rb;
+        }
+        if (lane < DROWS) sm.d4[lane] = rd;
+      }
+      if constexpr (PW) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) pw += __shfl_xor_sync(0xFFFFFFFFu, pw, o);
+          if (lane == 0) atomicAdd(p.power_sum + s, pw * pw_scale);
+      }
+      if (it_first + n_st == ips) {
+          const uint4* src = reinterpret_cast<const uint4*>(chunk + ((size_t)p.n - p.ht) * ES);
+          uint4* dst = reinterpret_cast<uint4*>((unsigned char*)p.tail_out + s * tail_bytes);
+          for (int i = lane; i < (int)(tail_bytes / 16); i += 32) dst[i] = src[i];
+      }
+      s++;
+      it_first = 0;
+      chunk += row_bytes;
+      tail += tail_bytes;
+    }
+}
+
+// host side: combined taps (double), limbs, banded matrix in fragment order, accumulator start values
+struct Tables {
+    uint2 b[2][NB][32];
+    int init[3];
+    double gain;
+    bool ok;
+    Tables() {
+        double gd[G];
+        for (int j = 0; j < G; j++) gd[j] = 0.0;
+        for (int k = 0; k < P25_TAPS_DECIM; k++)
+            for (int i = 0; i < P25_TAPS_FRONT; i++) gd[P25_DECIM_FRONT * k + i] += (double)P25_TAPS_DECIM_H[k] * (double)P25_TAPS_FRONT_H[i];
+        static int limb[G][3];
+        long long sum[3] = {0, 0, 0}, asum[3] = {0, 0, 0}, tsum = 0;
+        ok = true;
+        for (int j = 0; j < G; j++) {
+            const long long t = llround(gd[j] * (double)(1 << SCALE_LOG2));
+            long long v = t;
+            for (int l = 0; l < 3; l++) {
+                const long long d = ((v + 128) & 255) - 128;
+                limb[j][l] = (int)d;
+                v = (v - d) / 256;
+                sum[l] += d;
+                asum[l] += d < 0 ? -d : d;
+            }
+            if (v != 0) ok = false;                  // a tap that does not fit 24 bits
+            tsum += t;
+        }
+        for (int l = 0; l < 3; l++)
+            if (128 * asum[l] >= (1 << 22)) ok = false;   // an accumulator could leave the binade of 1.5 * 2^23
+        gain = (double)tsum / (double)(1 << SCALE_LOG2);
+        for (int l = 0; l < 3; l++) init[l] = 0x4B400000 - 128 * (int)sum[l];
+        for (int sk = 0; sk < 2; sk++)
+            for (int ks = 0; ks < KS; ks++)
+                for (int l = 0; l < 3; l++)
+                    for (int ln = 0; ln < 32; ln++) {
+                        const int n = ln >> 2, tig = ln & 3;
+                        unsigned w[2] = {0u, 0u};
+                        for (int h = 0; h < 2; h++)
+                            for (int bb = 0; bb < 4; bb++) {
+                                const int phi = 32 * ks + 16 * h + 4 * tig + bb;    // byte of the row window
+                                const int smp = phi >> 1, comp = phi & 1;
+                                const int d = smp - sk - D * (n >> 1);              // y[t] = sum_j g[j] X[50 t + 289 - j]
+                                int v = 0;
+                                if (comp == (n & 1) && d >= 0 && d < G) v = limb[G - 1 - d][l];
+                                w[h] |= (unsigned)(v & 255) << (8 * bb);
+                            }
+                        b[sk][ks * 3 + l][ln] = make_uint2(w[0], w[1]);
+                    }
+    }
+};
+static const Tables& tables() {
+    static const Tables t;
+    return t;
+}
+
+}  // namespace w50i
+
 unsigned p25cu_ddc_tail_len(int decimation) { return decimation == 50 ? Cfg<true>::HT : Cfg<false>::HT; }
 
 cudaError_t p25cu_ddc_upload_taps() {
@@ -1745,6 +2079,14 @@ cudaError_t p25cu_ddc_upload_taps() {
         const int4 q[3] = {make_int4(t.init[0], t.init[0], t.init[0], t.init[0]), make_int4(t.init[1], t.init[1], t.init[1], t.init[1]),
                            make_int4(t.init[2], t.init[2], t.init[2], t.init[2])};
         if ((e = cudaMemcpyToSymbol(w5i::g_init, q, sizeof(q))) != cudaSuccess) return e;
+    }
+    {
+        const w50i::Tables& t = w50i::tables();
+        if (!t.ok) return cudaErrorInvalidValue;
+        if ((e = cudaMemcpyToSymbol(w50i::g_btab, t.b, sizeof(w50i::g_btab))) != cudaSuccess) return e;
+        const int4 q[3] = {make_int4(t.init[0], t.init[0], t.init[0], t.init[0]), make_int4(t.init[1], t.init[1], t.init[1], t.init[1]),
+                           make_int4(t.init[2], t.init[2], t.init[2], t.init[2])};
+        if ((e = cudaMemcpyToSymbol(w50i::g_init, q, sizeof(q))) != cudaSuccess) return e;
     }
     return cudaMemcpyToSymbol(c_iq_lut, P25_IQ_LUT, sizeof(c_iq_lut));
 }
@@ -1838,6 +2180,22 @@ static cudaError_t launch_w5i(const DdcParams& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+static cudaError_t launch_w50i(const DdcParams& p, cudaStream_t st) {
+    const size_t smem = sizeof(w50i::WarpSm) * w50i::WARPS + sizeof(uint2) * w50i::NB * 32;
+    const unsigned ips = (p.n_out + w50i::NOUT - 1) / w50i::NOUT;
+    const unsigned long long total = (unsigned long long)p.n_streams * ips;
+    unsigned long long want = (total + 3) / 4;                 // at least ~4 iterations per warp (one warm-up each)
+    want = (want + w50i::WARPS - 1) / w50i::WARPS;
+    const unsigned grid = want < (unsigned long long)p.plan->grid_w50i ? (unsigned)(want ? want : 1) : (unsigned)p.plan->grid_w50i;
+    const w50i::Tables& t = w50i::tables();
+    const double sc = (double)(1 << w50i::SCALE_LOG2);
+    const float dc = (float)(0.5 * t.gain * tap_gain(P25_TAPS_CHAN_H, P25_TAPS_CHAN) * sc);
+    const float pw_scale = (float)(1.0 / (127.5 * 127.5) / (sc * sc));
+    if (p.power_sum) w50i::p25_ddc50_imma_kernel<true><<<grid, 32 * w50i::WARPS, smem, st>>>(p, ips, dc, pw_scale);
+    else w50i::p25_ddc50_imma_kernel<false><<<grid, 32 * w50i::WARPS, smem, st>>>(p, ips, dc, pw_scale);
+    return cudaGetLastError();
+}
+
 // Per-device setup (called once per device under the library's plan mutex, with that device current): opt every
 // kernel into its dynamic shared memory and size the persistent grids from the device's own occupancy.
 template <typename K>
@@ -1876,6 +2234,9 @@ cudaError_t p25cu_ddc_plan_device(P25DevPlan* plan) {
         const int per_sm = atoi(ev);
         if (per_sm > 0) plan->grid_w5i = n_sm * per_sm;
     }
+    const size_t smem_w50i = sizeof(w50i::WarpSm) * w50i::WARPS + sizeof(uint2) * w50i::NB * 32;
+    if ((e = plan_one(w50i::p25_ddc50_imma_kernel<true>, 32 * w50i::WARPS, smem_w50i, n_sm, &plan->grid_w50i)) != cudaSuccess) return e;
+    if ((e = plan_one(w50i::p25_ddc50_imma_kernel<false>, 32 * w50i::WARPS, smem_w50i, n_sm, &plan->grid_w50i)) != cudaSuccess) return e;
     const size_t atab = w5::ATAB_FLOATS * sizeof(float);
     if ((e = plan_one(w5::p25_ddc5_warp_kernel<U8, true>, 32 * w5::WARPS, sizeof(w5::WarpSm<U8, true>) * w5::WARPS + atab, n_sm, &plan->grid_w5m[U8])) != cudaSuccess) return e;
     if ((e = plan_one(w5::p25_ddc5_warp_kernel<CF, true>, 32 * w5::WARPS, sizeof(w5::WarpSm<CF, true>) * w5::WARPS + atab, n_sm, &plan->grid_w5m[CF])) != cudaSuccess) return e;
@@ -1911,8 +2272,12 @@ cudaError_t p25cu_launch_ddc(const DdcParams& p, int format, int decimation, cud
         return launch_fast<P25CU_FMT_CF32_IQ>(p, st);
     // u8 at 2.4 MS/s: any decimator phase (blocks are staged from their enclosing 16-byte group); like the /5 fast paths the
     // whole history must lie inside the stream (no byte encodes the zeros in front of a stream start)
-    if (decimation == 50 && format == P25CU_FMT_U8_IQ && p.aligned16 && p.n_out > 0 && p.a0 >= p.ht && p.ht == (unsigned)Cfg<true>::HT)
+    if (decimation == 50 && format == P25CU_FMT_U8_IQ && p.aligned16 && p.n_out > 0 && p.a0 >= p.ht && p.ht == (unsigned)Cfg<true>::HT) {
+        // both decimating stages on the integer tensor pipe (A/B switch P25CU_DDC50: 0 = the FFMA2 stream kernel)
+        static const int v50 = getenv("P25CU_DDC50") ? atoi(getenv("P25CU_DDC50")) : 1;
+        if ((v50 & 1) && p.n >= p.ht) return launch_w50i(p, st);
         return launch_fast<P25CU_FMT_U8_IQ>(p, st);
+    }
     if (decimation == 50)
         return format == P25CU_FMT_CF32_IQ ? launch<true, P25CU_FMT_CF32_IQ>(p, st) : launch<true, P25CU_FMT_U8_IQ>(p, st);
     return format == P25CU_FMT_CF32_IQ ? launch<false, P25CU_FMT_CF32_IQ>(p, st) : launch<false, P25CU_FMT_U8_IQ>(p, st);

@@ -87,6 +87,7 @@ struct P25DevPlan {
     int grid_fast5[2];            // fast5::p25_ddc5_fm_kernel<FMT>
     int grid_w5[2];               // w5::p25_ddc5_warp_kernel<FMT, false>
     int grid_w5m[2];              // ... with the channel filter on the tensor pipe
+    int grid_w50i;                // w50i::p25_ddc50_imma_kernel (u8 /50, both decimating stages on the integer tensor pipe)
     int grid_w5i;                 // w5i::p25_ddc5_imma_kernel (u8, decimator on the integer tensor pipe)
     int pfb_slots;                // resident CTAs of the channelizer kernel
 };
