@@ -1768,7 +1768,7 @@ constexpr int R = 4;
 constexpr int NOUT = 32 * R;                            // 128 outputs per warp iteration: two m-tiles of 16 rows x 4 outputs
 constexpr int XNEW = D * NOUT;                          // 6400 fresh input samples per iteration
 constexpr int XREAD = D * (NOUT - 1) + G;               // 6640 samples read
-constexpr int WARPS = 6;                                // one CTA per SM: 6 x 28 KB of slices + the B table
+constexpr int WARPS = 12;                               // one CTA per SM, three warps per scheduler: 12 x 15 KB + the B table
 constexpr int AL = 8, ES = 2;
 constexpr int XLEN = (XREAD + 2 * AL - 2) / AL * AL;    // 6648
 constexpr int KS = 28;                                  // k-steps: 1 + 150 + 290 = 441 samples <= 448
@@ -1781,11 +1781,12 @@ static_assert(XBYTES >= XLEN * ES && XNEW % (2 * AL) == 0 && 1 + D * 3 + G <= 16
 static_assert((P25_TAPS_CHAN - 1) % R == 0 && DROWS * R >= P25_BOXCAR - 1, "history rows");
 
 struct __align__(128) WarpSm {
-    unsigned char xs[2][XBYTES];
+    unsigned char xs[XBYTES];                   // ONE stage: the next slice is requested as soon as this one is consumed and
+                                                // lands while the other two warps of the scheduler own the tensor pipe
     float4 ydA[HROWS + 32 + 2];                 // 44 rows: ydB starts 16 banks further (half-warp stores: 32 banks)
     float4 ydB[HROWS + 32];
     float4 d4[DROWS + 32];
-    unsigned long long full[2];
+    unsigned long long full;
 };
 
 __device__ uint2 g_btab[2][NB][32];             // [skew & 1][fragment][lane]
@@ -1793,23 +1794,23 @@ __device__ int4 g_init[3];
 
 // bulk copy of the slice whose first input has logical index l0 (tail ++ chunk); the part in front of the tail
 // (l0 < 0: warm-up of a chunk's first piece) is skipped, the destination keeps its offset
-__device__ __forceinline__ void issue_slice(WarpSm& sm, int stage, int ht, int lend, const unsigned char* tail,
+__device__ __forceinline__ void issue_slice(WarpSm& sm, int ht, int lend, const unsigned char* tail,
                                             const unsigned char* chunk, int l0) {
     const int la0 = l0 & ~(AL - 1);
     const int la = max(la0, 0);
     const int lb = min(la0 + XLEN, lend);
-    unsigned char* dst = &sm.xs[stage][(la - la0) * ES];
+    unsigned char* dst = &sm.xs[(la - la0) * ES];
     if (la >= ht) {
         const unsigned bytes = (unsigned)(lb - la) * ES;
-        mbar_expect_tx(&sm.full[stage], bytes);
-        tma_load_1d(dst, chunk + (size_t)(la - ht) * ES, bytes, &sm.full[stage]);
+        mbar_expect_tx(&sm.full, bytes);
+        tma_load_1d(dst, chunk + (size_t)(la - ht) * ES, bytes, &sm.full);
         return;
     }
     const int t1 = min(lb, ht);
     const unsigned nt = (unsigned)(t1 - la), nc = (unsigned)(lb - t1);
-    mbar_expect_tx(&sm.full[stage], (nt + nc) * ES);
-    tma_load_1d(dst, tail + (size_t)la * ES, nt * ES, &sm.full[stage]);
-    if (nc) tma_load_1d(dst + nt * ES, chunk, nc * ES, &sm.full[stage]);
+    mbar_expect_tx(&sm.full, (nt + nc) * ES);
+    tma_load_1d(dst, tail + (size_t)la * ES, nt * ES, &sm.full);
+    if (nc) tma_load_1d(dst + nt * ES, chunk, nc * ES, &sm.full);
 }
 
 template <bool PW>
@@ -1825,11 +1826,10 @@ __global__ void __launch_bounds__(32 * WARPS, 1) p25_ddc50_imma_kernel(const Ddc
     const int skew = l_base & (AL - 1);                     // the same for every iteration of every stream
     for (int e = threadIdx.x; e < NB * 32; e += 32 * WARPS) btab[e] = (&g_btab[skew & 1][0][0])[e];
     if (lane == 0) {
-        mbar_init(&sm.full[0], 1);
-        mbar_init(&sm.full[1], 1);
+        mbar_init(&sm.full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = lane; i < 2 * XBYTES / 16; i += 32) reinterpret_cast<uint4*>(sm.xs)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = lane; i < XBYTES / 16; i += 32) reinterpret_cast<uint4*>(sm.xs)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = lane; i < HROWS + 32; i += 32) sm.ydA[i] = sm.ydB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = lane; i < DROWS + 32; i += 32) sm.d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zeroed stage buffers are overwritten by bulk copies
@@ -1846,8 +1846,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) p25_ddc50_imma_kernel(const Ddc
     const unsigned char* chunk = (const unsigned char*)p.iq + s * row_bytes;
     const unsigned char* tail = (const unsigned char*)p.tail_in + s * tail_bytes;
     if (lane == 0) {
-        issue_slice(sm, 0, ht, lend, tail, chunk, l_base + XNEW * (it_first - 1));
-        issue_slice(sm, 1, ht, lend, tail, chunk, l_base + XNEW * it_first);
+        issue_slice(sm, ht, lend, tail, chunk, l_base + XNEW * (it_first - 1));
     }
     // fragment geometry: mma rows g and g + 8 of m-tile mt read slice rows 16 mt + g and + 8 (400 bytes apart); the
     // lane's words of a k-step are t and t + 4 of its eight; (c0, c1) / (c2, c3) are output 4 row + t
@@ -1873,14 +1872,13 @@ __global__ void __launch_bounds__(32 * WARPS, 1) p25_ddc50_imma_kernel(const Ddc
       float pw = 0.f;
       for (int j = 0; j < npiece; j++, use++) {
         const int it = it_first - 1 + j;
-        const int stage = use & 1;
         const int nv = j ? min(n_out - NOUT * it, NOUT) : 0;
-        mbar_wait(&sm.full[stage], (use >> 1) & 1);
+        mbar_wait(&sm.full, use & 1);
 
         // ---- /50: 290-tap FIR on the raw bytes, 168 IMMA
         {
             int acc[2][3][4];
-            const unsigned xa = fast::smem_u32(sm.xs[stage]) + a_off;
+            const unsigned xa = fast::smem_u32(sm.xs) + a_off;
 #pragma unroll
             for (int ks = 0; ks < KS; ks++) {
                 unsigned a[2][4];
@@ -1913,10 +1911,10 @@ __global__ void __launch_bounds__(32 * WARPS, 1) p25_ddc50_imma_kernel(const Ddc
                     ydst[2 * (16 * mt + 8 * h)] = cfma(65536.f, f[2], cfma(256.f, f[1], f[0]));
                 }
         }
-        __syncwarp();                                                                 // S1: xs[stage] consumed, rows visible
+        __syncwarp();                                                                 // S1: xs consumed, rows visible
         if (lane == 0) {
-            if (j + 2 < npiece) issue_slice(sm, stage, ht, lend, tail, chunk, l_base + XNEW * (it + 2));
-            else if (left) issue_slice(sm, stage, ht, lend, tail + tail_bytes, chunk + row_bytes, l_base + XNEW * (j + 1 - npiece));
+            if (j + 1 < npiece) issue_slice(sm, ht, lend, tail, chunk, l_base + XNEW * (it + 1));
+            else if (left) issue_slice(sm, ht, lend, tail + tail_bytes, chunk + row_bytes, l_base - XNEW);
         }
 
         // ---- channel-select FIR: outputs 4 lane + r, window = rows lane .. lane + 10 (44 samples, s = 40 + r - k)
