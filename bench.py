@@ -99,7 +99,8 @@ class Workload:
         else:
             u8 = name == "cfg2u8"
             self.streams, self.fs, self.decim, self.fmt, self.scaling = STREAMS_PER_GPU, FS, DECIM, "u8" if u8 else "cf32", "weak"
-            self.kernel = f"fast::p25_ddc_fm_stream_kernel<{self.fmt}> (/50)"
+            self.kernel = ("w50i::p25_ddc50_imma_kernel (u8 /50: both decimating stages as one 290-tap FIR on the integer tensor pipe)"
+                           if u8 else "fast::p25_ddc_fm_stream_kernel<cf32> (/50)")
             self.desc = ("configs[1]: 1024 synthetic P25 control-channel IQ streams per GPU, " + ("u8" if u8 else "cf32") +
                          " 2.4 MS/s, 360000 samples (150 ms) per stream per step, /50 -> 48 kHz, C4FM demod + frame sync + NID/TSBK decode")
         self.bps = 2 if self.fmt == "u8" else 8
@@ -606,7 +607,8 @@ def summarise(wl: Workload, m: dict, world: int, K: int, hbm: float, hbm_src: st
     achieved = alg / (m["ddc_ms"] * 1e-3) / 1e9
     roof = {"kernel": wl.kernel, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
             "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": m["ddc_ms"]}
-    tf = {"cfg2": "ddc_fm_traffic.json", "cfg5": "ddc5_u8_imma_traffic.json", "cfg3": "pfb_traffic.json"}.get(wl.name)
+    tf = {"cfg2": "ddc_fm_traffic.json", "cfg2u8": "ddc50_u8_imma_traffic.json", "cfg5": "ddc5_u8_imma_traffic.json",
+          "cfg3": "pfb_traffic.json"}.get(wl.name)
     if tf:
         try:
             with open(os.path.join(ROOT, "profiles", tf)) as f:
@@ -624,6 +626,11 @@ def summarise(wl: Workload, m: dict, world: int, K: int, hbm: float, hbm_src: st
             fma = 2 * 41
             roof["tensor_int8_tops"] = 2.0 * 36 * 16 * 8 * 32 / 256 * wl.streams * (n // wl.decim) / (m["ddc_ms"] * 1e-3) / 1e12
             roof["tensor_int8_peak_tops"] = pipe_peak("mma_sync_u8s8_k32_tops")   # legacy mma.sync rate, tools/pipe_peaks.cu
+        if wl.decim == 50 and wl.fmt == "u8":
+            # 168 x m16n8k32 per 128 outputs (the 290-tap /50 FIR on the raw bytes, three limbs); channel filter on FFMA2
+            fma = 2 * 41
+            roof["tensor_int8_tops"] = 2.0 * 168 * 16 * 8 * 32 / 128 * wl.streams * (n // wl.decim) / (m["ddc_ms"] * 1e-3) / 1e12
+            roof["tensor_int8_peak_tops"] = pipe_peak("mma_sync_u8s8_k32_tops")
         flops = 2.0 * fma * wl.streams * (n // wl.decim)
         roof["fp32_tflops"] = flops / (m["ddc_ms"] * 1e-3) / 1e12
         if fp32:

@@ -127,3 +127,88 @@ def decimate_iteration(xs: np.ndarray, skew: int, taps: np.ndarray):
                     words.append(q * 37 * 4 + row * 4 + 2 * half)
                 store_words.append(np.array(words))
     return yf, load_banks, store_words
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# u8 /50 (`w50i::p25_ddc50_imma_kernel`): the /10 front stage and the /5 decimator as ONE 290-tap FIR on the raw bytes.
+# Rows are 200 samples (400 bytes) apart and hold four outputs (one n-tile), 28 k-steps x 3 limbs per m-tile.
+# ---------------------------------------------------------------------------------------------------------------------
+D50, G50, KS50, SCALE50 = 50, 290, 28, 28
+
+
+def combined_taps(hf: np.ndarray, hd: np.ndarray) -> np.ndarray:
+    """g[10 k + i] = hd[k] hf[i] in float64 from the float32 tap sets (yd[t] = sum_j g[j] X[50 t + 49 - j])."""
+    g = np.zeros(len(hf) + 10 * (len(hd) - 1))
+    for k, h in enumerate(hd.astype(np.float64)):
+        g[10 * k: 10 * k + len(hf)] += h * hf.astype(np.float64)
+    return g
+
+
+def limbs50(g: np.ndarray):
+    out = np.zeros((len(g), 3), dtype=np.int64)
+    for j, h in enumerate(g):
+        v = int(np.round(float(h) * (1 << SCALE50)))
+        for l in range(3):
+            d = ((v + 128) & 255) - 128
+            out[j, l] = d
+            v = (v - d) // 256
+        assert v == 0, "tap does not fit 24 bits"
+    return out
+
+
+def b_table50(lb: np.ndarray, sk: int) -> np.ndarray:
+    tab = np.zeros((KS50, 3, 32, 2, 4), dtype=np.int64)
+    for ks in range(KS50):
+        for l in range(3):
+            for lane in range(32):
+                n, t = lane >> 2, lane & 3
+                for h in range(2):
+                    for bb in range(4):
+                        phi = 32 * ks + 16 * h + 4 * t + bb
+                        smp, comp = phi >> 1, phi & 1
+                        d = smp - sk - D50 * (n >> 1)
+                        if comp == (n & 1) and 0 <= d < G50:
+                            tab[ks, l, lane, h, bb] = lb[G50 - 1 - d, l]
+    return tab
+
+
+def decimate50_iteration(xs: np.ndarray, skew: int, g: np.ndarray):
+    """One warp iteration (128 outputs).  xs: staged slice bytes from its 16-byte aligned start; the first sample of the
+    first output's 290-sample window sits `skew` samples (0..7) into it.  Returns (y[128][2] float32, load banks, stores)."""
+    lb = limbs50(g)
+    tab = b_table50(lb, skew & 1)
+    assert all(128 * int(np.abs(lb[:, l]).sum()) < (1 << 22) for l in range(3)), "accumulators stay in the magic binade"
+    init = [MAGIC - 128 * int(lb[:, l].sum()) for l in range(3)]
+    acc = np.zeros((2, 3, 32, 4), dtype=np.int64) + np.array(init, dtype=np.int64)[None, :, None, None]
+    lane = np.arange(32)
+    gq, t = lane >> 2, lane & 3
+    a_off = 400 * gq + 4 * (skew >> 1) + 4 * t
+    load_banks = []
+    for ks in range(KS50):
+        for mt in range(2):
+            ad = a_off + 6400 * mt + 32 * ks
+            a_frag = np.zeros((32, 4, 4), dtype=np.int64)
+            for r, off in enumerate((0, 3200, 16, 3216)):
+                for ln in range(32):
+                    a_frag[ln, r] = xs[ad[ln] + off: ad[ln] + off + 4]
+                load_banks.append(((ad + off) // 4) % 32)
+            for l in range(3):
+                mma_u8s8(acc[mt, l], a_frag, tab[ks, l])
+    yf = np.zeros((128, 2), dtype=np.float32)
+    stores = []
+    for mt in range(2):
+        for h in range(2):
+            words = []
+            for ln in range(32):
+                o = 4 * (16 * mt + gq[ln] + 8 * h) + t[ln]
+                f = []
+                for l in range(3):
+                    bits = acc[mt, l, ln, 2 * h: 2 * h + 2]
+                    assert np.all(np.abs(bits - MAGIC) < (1 << 22))
+                    f.append((np.array(bits, dtype=np.uint32).view(np.float32) - np.float32(12582912.0)).astype(np.float32))
+                inner = (np.float64(f[1]) * 256.0 + np.float64(f[0])).astype(np.float32)
+                yf[o] = (np.float64(f[2]) * 65536.0 + np.float64(inner)).astype(np.float32)
+                arr, half = t[ln] >> 1, t[ln] & 1                     # ydA (44 rows) | ydB
+                words.append(arr * 44 * 4 + (10 + 16 * mt + gq[ln] + 8 * h) * 4 + 2 * half)
+            stores.append(np.array(words))
+    return yf, load_banks, stores

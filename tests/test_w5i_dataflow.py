@@ -47,3 +47,33 @@ def test_iteration_equals_the_fir(skew):
         for half in (words[:16], words[16:]):
             banks = np.concatenate([half % 32, (half + 1) % 32])
             assert len(set(banks.tolist())) == 32
+
+
+@pytest.mark.parametrize("skew", [0, 3, 6])
+def test_combined_50_iteration_equals_the_two_stage_chain(skew):
+    """w50i: the 290-tap integer FIR on the bytes equals front (/10, 50 taps) then decimator (/5, 25 taps) in float64."""
+    rng = np.random.default_rng(10 + skew)
+    hf, hd = spec.taps_front().astype(np.float32), spec.taps_decim().astype(np.float32)
+    g = df.combined_taps(hf, hd)
+    assert len(g) == df.G50 and abs(g.sum() - hf.astype(np.float64).sum() * hd.astype(np.float64).sum()) < 1e-12
+    xs = rng.integers(0, 256, size=13312, dtype=np.int64)
+    yf, load_banks, stores = df.decimate50_iteration(xs, skew, g)
+    x = (xs[0::2] - 128) + 1j * (xs[1::2] - 128)
+    # two-stage definition on the same samples: f[n] = sum_i hf[i] X[10 n + 9 - i], yd[t] = sum_k hd[k] f[5 t + 4 - k],
+    # X relative to the block base = window start + 240
+    base = skew + 240
+    for o in (0, 1, 63, 64, 100, 127):
+        acc = 0.0
+        for k in range(25):
+            n = 5 * o + 4 - k
+            idx = base + 10 * n + 9 - np.arange(50)
+            acc += float(hd[k]) * np.dot(hf.astype(np.float64), x[idx])
+        ref = acc * 2.0 ** df.SCALE50
+        got = float(yf[o, 0]) + 1j * float(yf[o, 1])
+        assert abs(got - ref) <= 128 * df.G50 * 0.5 * 1.5 + abs(ref) * 2.0 ** -22, (o, got, ref)
+    for banks in load_banks:
+        assert len(set(banks.tolist())) == 32
+    for words in stores:
+        for half in (words[:16], words[16:]):
+            banks = np.concatenate([half % 32, (half + 1) % 32])
+            assert len(set(banks.tolist())) == 32
