@@ -509,3 +509,44 @@ def test_channelizer_is_invariant_under_chunking(p25, oracle):
         assert np.max(np.abs(whole[1][k, 200:] - ragged[1][k, 200:])) < BB_TOL, k
     busy = lambda e: e[np.isin(e["stream"], (7, 1530))]
     assert events_key(busy(whole[3])) == events_key(busy(ragged[3])) and len(busy(whole[3])) >= 8, len(busy(whole[3]))
+
+
+# ------------------------------------------------------------------ integer-tensor-pipe decimators: chunk phases and edge sizes
+@pytest.mark.parametrize("dec,chunks", [
+    (5, [16384, 1312, 1320, 2568, 5128, 20000, 1312, 8]),          # 1312 = the carried tail: the smallest fast-path chunk
+    (50, [16384, 3264, 3272, 6648, 12808, 40000, 3264, 8]),
+])
+def test_u8_imma_kernels_chunk_phases_and_minimal_chunks(p25, oracle, dec, chunks):
+    """w5i / w50i (u8, decimator stages as u8 x s8 mma.sync on the raw bytes): a chunk sequence that walks the slice's
+    alignment inside its 16-byte group through every value it can take, with chunks as short as the carried tail (one warp
+    iteration per stream: warm-up + one partial iteration), one of a single 16-byte group (generic kernel between two
+    fast ones), seven streams (a ragged share of the flattened work space), power requested on alternate chunks (both
+    template instantiations).  Baseband <= 1e-4 of the oracle's, power <= 0.01 dB."""
+    fs = 240_000 * (dec // 5)
+    S_ = 7
+    total = sum(chunks)
+    rows = []
+    for s in range(S_):
+        st = tx.control_channel(700 + s, 3)
+        iq = tx.modulate_iq(st.dibits, fs, snr_db=22, cfo_hz=60.0 * (s - 3), seed=40 + s, amplitude=[0.02, 0.1, 0.3, 0.5, 0.7, 0.9, 0.97][s])
+        assert len(iq) >= total
+        rows.append(tx.iq_to_u8(iq[:total]))
+    data = np.stack(rows)
+    ctx = p25.Context(S_, fmt=p25.FMT_U8_IQ, decimation=dec, max_chunk_samples=max(chunks))
+    chains = [oracle.DemodChain(oracle.FMT_U8, dec == 50) for _ in range(S_)]
+    pos, worst = 0, 0.0
+    for i, m in enumerate(chunks):
+        part = np.ascontiguousarray(data[:, 2 * pos: 2 * (pos + m)])
+        want_pw = i % 2 == 1
+        bb, n_out, pw = ctx.demod(part, m, want_power=want_pw)
+        for s in range(S_):
+            ref = chains[s].feed(part[s], want_power=want_pw)
+            if want_pw:
+                ref, pref = ref
+                assert abs(pw[s] - pref) < 1e-2, (i, s, pw[s], pref)
+            assert len(ref) == n_out
+            if n_out:
+                worst = max(worst, float(np.max(np.abs(bb[s] - ref))))
+        pos += m
+    assert worst < BB_TOL, worst
+    ctx.close()
