@@ -1852,11 +1852,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) p25_ddc50_imma_kernel(const Ddc
     // lane's words of a k-step are t and t + 4 of its eight; (c0, c1) / (c2, c3) are output 4 row + t
     const int g = lane >> 2, tig = lane & 3;
     const unsigned a_off = 400u * g + 4u * (skew >> 1) + 4u * tig;
-    // B fragments: the column of an output's Q component is the column of its I component one byte further along k (taps
-    // on the odd instead of the even bytes), so lanes of odd columns read their even neighbour's entry -- the warp then
-    // touches 128 instead of 256 bytes per fragment (one shared-memory wavefront) -- and shift it by eight bits
-    const uint2* const bl = btab + (lane & ~4);
-    const unsigned bsh = (lane & 4) ? 8u : 0u;
+    const uint2* const bl = btab + lane;
     float2* const ydst = reinterpret_cast<float2*>(tig < 2 ? &sm.ydA[HROWS + g] : &sm.ydB[HROWS + g]) + (tig & 1);
     const float2 unmagic = make_float2(-12582912.f, -12582912.f);
     float2 c_carry = make_float2(0.f, 0.f);
@@ -1896,9 +1892,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) p25_ddc50_imma_kernel(const Ddc
                 }
 #pragma unroll
                 for (int l = 0; l < 3; l++) {
-                    uint2 b = bl[32 * (ks * 3 + l)];
-                    b.x <<= bsh;
-                    b.y <<= bsh;
+                    const uint2 b = bl[32 * (ks * 3 + l)];
 #pragma unroll
                     for (int mt = 0; mt < 2; mt++) {
                         if (ks == 0) imma0(acc[mt][l], a[mt], b, init[l]);
