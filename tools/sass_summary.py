@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """sass_summary.py -- per-kernel SASS evidence of libp25cu.so (no GPU needed): instruction counts of the mnemonics that
 tell a Blackwell-native streaming kernel from a recompiled one (B200_PROFILING.md: UBLKCP / UTMALDG = TMA bulk copies,
-SYNCS = mbarrier, UCGABAR = cluster barrier, FFMA2 / FADD2 / FMUL2 = packed FP32, UTC*MMA / LDTM / STTM = tcgen05 + TMEM, HMMA = legacy mma.sync), plus registers,
+SYNCS = mbarrier, UCGABAR = cluster barrier, FFMA2 / FADD2 / FMUL2 = packed FP32, UTC*MMA / LDTM / STTM = tcgen05 + TMEM, HMMA / IMMA = legacy mma.sync, IMMA on the raw u8 IQ bytes), plus registers,
 spills and shared memory from `cuobjdump -res-usage`.
 
     python tools/sass_summary.py [p25rx_b200/libp25cu.so] > profiles/sass_summary.txt
@@ -13,7 +13,7 @@ import sys
 from collections import Counter, OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-WATCH = ["FFMA2", "FFMA", "FADD2", "FMUL2", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "UTCHMMA", "UTCQMMA", "UTCIMMA", "LDTM", "STTM", "HMMA",
+WATCH = ["FFMA2", "FFMA", "FADD2", "FMUL2", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "UTCHMMA", "UTCQMMA", "UTCIMMA", "LDTM", "STTM", "HMMA", "IMMA",
          "UCGABAR_ARV", "UCGABAR_WAIT", "PRMT", "LDS", "STS", "ST", "LDG", "STG", "SHFL", "BAR", "REDUX", "ATOMG", "RED", "MUFU", "IDP"]
 
 
