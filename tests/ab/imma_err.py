@@ -7,7 +7,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # tests/ab/ -> repository root
 for p in (ROOT, os.path.join(ROOT, "spec")):
     sys.path.insert(0, p)
 import p25rx_b200 as p25           # noqa: E402

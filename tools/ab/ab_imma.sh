@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 {
 for v in 3 11; do
   echo "== P25CU_DDC5=$v"
-  P25CU_DDC5=$v python tools/ab/imma_err.py 2>&1 | tail -1
+  P25CU_DDC5=$v python tests/ab/imma_err.py 2>&1 | tail -1
 done
 echo "== parity subset with P25CU_DDC5=11"
 P25CU_DDC5=11 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "demod or process or cfg5 or cfg4 or golden or full_size" 2>&1 | tail -5

@@ -9,5 +9,5 @@ echo "== racecheck: -k 'golden or prefilter or pdu or invariant_under_chunking'"
 timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -m gpu -q -k "golden or prefilter or pdu or invariant_under_chunking" 2>&1 | grep -E "passed|failed|RACECHECK SUMMARY|FAILED" | tail -6
 echo "== synccheck: -k 'golden or prefilter or invariant_under_chunking'"
 timeout 600 compute-sanitizer --tool synccheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -m gpu -q -k "golden or prefilter or invariant_under_chunking" 2>&1 | grep -E "passed|failed|ERROR SUMMARY|FAILED" | tail -5
-echo "== memcheck: tools/ab/dbg_poll.py (records / packed synchronous / packed asynchronous against the oracle)"
-compute-sanitizer --tool memcheck python tools/ab/dbg_poll.py 2>&1 | grep -E "differing|ERROR SUMMARY"
+echo "== memcheck: tests/ab/dbg_poll.py (records / packed synchronous / packed asynchronous against the oracle)"
+compute-sanitizer --tool memcheck python tests/ab/dbg_poll.py 2>&1 | grep -E "differing|ERROR SUMMARY"
