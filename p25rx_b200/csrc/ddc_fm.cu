@@ -29,6 +29,7 @@
 #include <stdlib.h>
 
 #include "p25cu_internal.cuh"
+#include "p25_imma_tables.h"
 
 __constant__ float c_taps_front[P25_TAPS_FRONT];
 __constant__ float c_taps_decim[P25_TAPS_DECIM];
@@ -1684,49 +1685,12 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) p25_ddc5_imma_kernel(const D
     }
 }
 
-// host side: the banded tap matrix in fragment order, and the accumulator start values
-struct Tables {
-    uint2 b[4][NB][32];
-    int init[3];
-    double gain;                                // sum of the quantised taps / 2^25 (DC gain of the integer decimator)
-    Tables() {
-        int limb[P25_TAPS_DECIM][3];
-        long long sum[3] = {0, 0, 0}, tsum = 0;
-        for (int k = 0; k < P25_TAPS_DECIM; k++) {
-            const long long t = llround((double)P25_TAPS_DECIM_H[k] * (double)(1 << SCALE_LOG2));
-            long long v = t;
-            for (int l = 0; l < 3; l++) {
-                const long long d = ((v + 128) & 255) - 128;    // balanced digit in [-128, 127]
-                limb[k][l] = (int)d;
-                v = (v - d) / 256;
-                sum[l] += d;
-            }
-            tsum += t;                          // v == 0 here: |t| < 2^23 for this tap set
-        }
-        gain = (double)tsum / (double)(1 << SCALE_LOG2);
-        for (int l = 0; l < 3; l++) init[l] = 0x4B400000 - 128 * (int)sum[l];
-        for (int sk = 0; sk < 4; sk++)
-            for (int nt = 0; nt < 2; nt++)
-                for (int jj = 0; jj < 3; jj++)
-                    for (int l = 0; l < 3; l++)
-                        for (int ln = 0; ln < 32; ln++) {
-                            const int n = ln >> 2, tig = ln & 3, ks = nt + jj;
-                            unsigned w[2] = {0u, 0u};
-                            for (int h = 0; h < 2; h++)
-                                for (int bb = 0; bb < 4; bb++) {
-                                    const int phi = 32 * ks + 16 * h + 4 * tig + bb;    // byte of the row window
-                                    const int smp = phi >> 1, comp = phi & 1;
-                                    const int d = smp - sk - 5 * (4 * nt + (n >> 1));
-                                    int v = 0;
-                                    if (comp == (n & 1) && d >= 0 && d < P25_TAPS_DECIM) v = limb[P25_TAPS_DECIM - 1 - d][l];
-                                    w[h] |= (unsigned)(v & 255) << (8 * bb);
-                                }
-                            b[sk][(nt * 3 + jj) * 3 + l][ln] = make_uint2(w[0], w[1]);
-                        }
-    }
-};
+// host side: the banded tap matrix in fragment order and the accumulator start values (p25_imma_tables.h, plain C++ so that
+// the CPU suite can check the very tables this library uploads against the numpy dataflow model)
+using Tables = p25imma::Tables5;
+static_assert(NB == p25imma::NB5 && SCALE_LOG2 == p25imma::SCALE5 && sizeof(g_btab) == sizeof(Tables::b), "table geometry");
 static const Tables& tables() {
-    static const Tables t;
+    static const Tables t(P25_TAPS_DECIM_H);
     return t;
 }
 
@@ -2007,58 +1971,12 @@ __global__ void __launch_bounds__(32 * WARPS, 1) p25_ddc50_imma_kernel(const Ddc
     }
 }
 
-// host side: combined taps (double), limbs, banded matrix in fragment order, accumulator start values
-struct Tables {
-    uint2 b[2][NB][32];
-    int init[3];
-    double gain;
-    bool ok;
-    Tables() {
-        double gd[G];
-        for (int j = 0; j < G; j++) gd[j] = 0.0;
-        for (int k = 0; k < P25_TAPS_DECIM; k++)
-            for (int i = 0; i < P25_TAPS_FRONT; i++) gd[P25_DECIM_FRONT * k + i] += (double)P25_TAPS_DECIM_H[k] * (double)P25_TAPS_FRONT_H[i];
-        static int limb[G][3];
-        long long sum[3] = {0, 0, 0}, asum[3] = {0, 0, 0}, tsum = 0;
-        ok = true;
-        for (int j = 0; j < G; j++) {
-            const long long t = llround(gd[j] * (double)(1 << SCALE_LOG2));
-            long long v = t;
-            for (int l = 0; l < 3; l++) {
-                const long long d = ((v + 128) & 255) - 128;
-                limb[j][l] = (int)d;
-                v = (v - d) / 256;
-                sum[l] += d;
-                asum[l] += d < 0 ? -d : d;
-            }
-            if (v != 0) ok = false;                  // a tap that does not fit 24 bits
-            tsum += t;
-        }
-        for (int l = 0; l < 3; l++)
-            if (128 * asum[l] >= (1 << 22)) ok = false;   // an accumulator could leave the binade of 1.5 * 2^23
-        gain = (double)tsum / (double)(1 << SCALE_LOG2);
-        for (int l = 0; l < 3; l++) init[l] = 0x4B400000 - 128 * (int)sum[l];
-        for (int sk = 0; sk < 2; sk++)
-            for (int ks = 0; ks < KS; ks++)
-                for (int l = 0; l < 3; l++)
-                    for (int ln = 0; ln < 32; ln++) {
-                        const int n = ln >> 2, tig = ln & 3;
-                        unsigned w[2] = {0u, 0u};
-                        for (int h = 0; h < 2; h++)
-                            for (int bb = 0; bb < 4; bb++) {
-                                const int phi = 32 * ks + 16 * h + 4 * tig + bb;    // byte of the row window
-                                const int smp = phi >> 1, comp = phi & 1;
-                                const int d = smp - sk - D * (n >> 1);              // y[t] = sum_j g[j] X[50 t + 289 - j]
-                                int v = 0;
-                                if (comp == (n & 1) && d >= 0 && d < G) v = limb[G - 1 - d][l];
-                                w[h] |= (unsigned)(v & 255) << (8 * bb);
-                            }
-                        b[sk][ks * 3 + l][ln] = make_uint2(w[0], w[1]);
-                    }
-    }
-};
+// host side: combined taps (double), limbs, banded matrix in fragment order, accumulator start values (p25_imma_tables.h)
+using Tables = p25imma::Tables50;
+static_assert(NB == p25imma::NB50 && KS == p25imma::KS50 && SCALE_LOG2 == p25imma::SCALE50 && G == p25imma::G50 &&
+              sizeof(g_btab) == sizeof(Tables::b), "table geometry");
 static const Tables& tables() {
-    static const Tables t;
+    static const Tables t(P25_TAPS_FRONT_H, P25_TAPS_DECIM_H);
     return t;
 }
 
@@ -2071,9 +1989,10 @@ cudaError_t p25cu_ddc_upload_taps() {
     if ((e = cudaMemcpyToSymbol(c_taps_front, P25_TAPS_FRONT_H, sizeof(c_taps_front))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_taps_decim, P25_TAPS_DECIM_H, sizeof(c_taps_decim))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_taps_chan, P25_TAPS_CHAN_H, sizeof(c_taps_chan))) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(w5i::g_btab, w5i::tables().b, sizeof(w5i::g_btab))) != cudaSuccess) return e;
     {
         const w5i::Tables& t = w5i::tables();
+        if (!t.ok) return cudaErrorInvalidValue;
+        if ((e = cudaMemcpyToSymbol(w5i::g_btab, t.b, sizeof(w5i::g_btab))) != cudaSuccess) return e;
         const int4 q[3] = {make_int4(t.init[0], t.init[0], t.init[0], t.init[0]), make_int4(t.init[1], t.init[1], t.init[1], t.init[1]),
                            make_int4(t.init[2], t.init[2], t.init[2], t.init[2])};
         if ((e = cudaMemcpyToSymbol(w5i::g_init, q, sizeof(q))) != cudaSuccess) return e;

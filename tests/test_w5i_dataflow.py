@@ -77,3 +77,48 @@ def test_combined_50_iteration_equals_the_two_stage_chain(skew):
         for half in (words[:16], words[16:]):
             banks = np.concatenate([half % 32, (half + 1) % 32])
             assert len(set(banks.tolist())) == 32
+
+
+# ------------------------------------------------------------------ the library's own tables (p25_imma_tables.h) vs the model
+@pytest.fixture(scope="module")
+def imma_hostcheck():
+    """tests/hostcheck: the header ddc_fm.cu builds its table uploads from, compiled for the host -- test harness only."""
+    import ctypes as C
+    import os
+    import subprocess
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck")
+    so = os.path.join(d, "libimma_hostcheck.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", so, os.path.join(d, "imma_hostcheck.cpp")])
+    return C.CDLL(so)
+
+
+def _pack(tab):
+    """model fragments [..., lane, reg, byte] (signed) -> words [..., lane, reg] like the library's Frag entries"""
+    b = (tab & 255).astype(np.uint64)
+    return (b[..., 0] | (b[..., 1] << 8) | (b[..., 2] << 16) | (b[..., 3] << 24)).astype(np.uint32)
+
+
+def test_library_tables_equal_the_model(imma_hostcheck):
+    import ctypes as C
+    taps = _taps()
+    lb, tsum = df.limbs(taps)
+    out = np.zeros((4, 18, 32, 2), dtype=np.uint32)
+    init = np.zeros(3, dtype=np.int32)
+    gain = C.c_double()
+    assert imma_hostcheck.hc_imma5(out.ctypes.data_as(C.c_void_p), init.ctypes.data_as(C.c_void_p), C.byref(gain)) == 1
+    for sk in range(4):
+        model = _pack(df.b_table(lb, sk)).reshape(18, 32, 2)       # [nt][jj][limb] -> (nt * 3 + jj) * 3 + limb
+        assert np.array_equal(out[sk], model), sk
+    assert init.tolist() == [df.MAGIC - 128 * int(lb[:, l].sum()) for l in range(3)]
+    assert gain.value == tsum / 2.0 ** df.SCALE_LOG2
+
+    g = df.combined_taps(spec.taps_front().astype(np.float32), taps)
+    lb50 = df.limbs50(g)
+    out50 = np.zeros((2, 84, 32, 2), dtype=np.uint32)
+    assert imma_hostcheck.hc_imma50(out50.ctypes.data_as(C.c_void_p), init.ctypes.data_as(C.c_void_p), C.byref(gain)) == 1
+    for sk in range(2):
+        model = _pack(df.b_table50(lb50, sk)).reshape(84, 32, 2)   # [ks][limb] -> ks * 3 + limb
+        assert np.array_equal(out50[sk], model), sk
+    assert init.tolist() == [df.MAGIC - 128 * int(lb50[:, l].sum()) for l in range(3)]
+    t50 = lb50[:, 0] + 256 * lb50[:, 1] + 65536 * lb50[:, 2]
+    assert gain.value == int(t50.sum()) / 2.0 ** df.SCALE50
