@@ -122,3 +122,41 @@ def test_library_tables_equal_the_model(imma_hostcheck):
     assert init.tolist() == [df.MAGIC - 128 * int(lb50[:, l].sum()) for l in range(3)]
     t50 = lb50[:, 0] + 256 * lb50[:, 1] + 65536 * lb50[:, 2]
     assert gain.value == int(t50.sum()) / 2.0 ** df.SCALE50
+
+
+# ------------------------------------------------------------------ slice arithmetic: every kept output sees only copied bytes
+@pytest.mark.parametrize("name,D,T,NOUT,XLEN,ht,clamp", [
+    ("w5i", 5, 25, 256, 1312, 1312, False),        # ddc_fm.cu: w5i::issue_slice (no clamp: a slice never starts in front of the tail)
+    ("w50i", 50, 290, 128, 6648, 3264, True),      # w50i::issue_slice (the part in front of the tail is skipped)
+])
+def test_slices_cover_every_kept_output(name, D, T, NOUT, XLEN, ht, clamp):
+    """The fast kernels copy [la, lb) of the logical input (tail ++ chunk) per warp iteration.  Restated here: for any chunk
+    position and length the windows of all stored outputs, and of the last 50 outputs of a warm-up iteration (40 channel
+    filter + 10 boxcar histories), lie inside the copied range -- so the bytes that are not copied (in front of the tail, past
+    the chunk's end) only ever reach outputs nobody keeps."""
+    rng = np.random.default_rng(5)
+    cases = [(ht, ht), (ht, ht + 8), (ht + 3, 16384), (12345 * 8 + 1, 360000)]
+    cases += [(int(ht + rng.integers(0, 100000)), int(8 * rng.integers(ht // 8, 6000))) for _ in range(60)]
+    for a0, n in cases:
+        newest0 = D - 1                                    # output m's newest input is D m + D - 1
+        m0 = -((newest0 - a0) // D)                        # first m with D m + D - 1 >= a0
+        m_end = -((newest0 - (a0 + n)) // D)               # first m beyond the chunk
+        n_out = m_end - m0
+        assert n_out > 0
+        l_base = D * m0 - a0 - (T - D) + ht                # logical index of output m0's oldest input
+        assert 0 <= l_base and l_base + T - 1 < ht + n and (D * m0 + D - 1 - a0) in range(D)
+        lend = ht + n
+        ips = -(-n_out // NOUT)
+        XNEW = D * NOUT
+        for it in range(-1, ips):
+            l0 = l_base + XNEW * it
+            la0 = l0 & ~7
+            la = max(la0, 0) if clamp else la0
+            lb = min(la0 + XLEN, lend)
+            assert la >= 0 and lb > la and (lb - la) % 8 == 0, (name, a0, n, it)
+            if it >= 0:                                    # a stored iteration: outputs o < nv
+                nv = min(n_out - NOUT * it, NOUT)
+                assert l0 >= la and l0 + D * (nv - 1) + T - 1 < lb, (name, a0, n, it)
+            if it + 1 < ips:                               # this iteration may be the warm-up of a piece starting at it + 1
+                first = l0 + D * (NOUT - 50)
+                assert first >= la and l0 + D * (NOUT - 1) + T - 1 < lb, (name, a0, n, it)
