@@ -21,11 +21,15 @@
 //   fast::p25_ddc_fm_stream_kernel    cf32, /50 (the bench kernel): TMA bulk copies into a two-stage
 //                                     ring, FFMA2 FIRs, persistent grid with a static + ticket work split.
 //   fast5::p25_ddc5_fm_kernel<FMT>    /5 tile kernel: independent tiles with their own warm-up.
-//   w5::p25_ddc5_warp_kernel<FMT>     /5 warp-autonomous kernel (default for u8 and cf32): every warp is
+//   w5::p25_ddc5_warp_kernel<FMT>     /5 warp-autonomous kernel (default for cf32): every warp is
 //                                     its own pipeline, no CTA barriers.
+//   w5i::p25_ddc5_imma_kernel         u8 /5 (default): the warp kernel with the /5 decimator as exact integer
+//                                     products on the tensor pipe (mma.sync u8 x s8 on the raw IQ bytes).
+//   w50i::p25_ddc50_imma_kernel       u8 /50 (default): both decimating stages as one 290-tap integer FIR.
 //
-// Algorithmic traffic: 8 + 4/D bytes per cf32 input sample, 2 + 4/D per u8 sample; the /50
-// kernel is HBM-bound, the /5 kernels are bound by the FP32 pipe (66 complex-by-real taps per output).
+// Algorithmic traffic: 8 + 4/D bytes per cf32 input sample, 2 + 4/D per u8 sample; the cf32 /50
+// kernel is HBM-bound (97 %), u8 /50 runs at 78 % of HBM, the /5 kernels are bound by issue slots and the FP32 pipe
+// (62 complex-by-real taps per output; u8: 41 once the decimator is on the tensor pipe).
 #include <stdlib.h>
 
 #include "p25cu_internal.cuh"
